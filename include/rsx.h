@@ -1,0 +1,142 @@
+/*
+ * rsx.h -- C ABI of librsx.so: the B200 (sm_100a) LSD radix-sort hot path.
+ *
+ * This is the drop-in boundary.  The reference (eloj/radix-sorting) has no FFI: its surface
+ * is two header-only C++ templates.  Each entry point below names the reference interface it
+ * replaces; include/radix_sort.hpp, include/radix_sort_rank.hpp and
+ * include/radix_sort_basic_kdf.hpp re-create the reference's template signatures on top of
+ * these calls (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Plain pointers and sizes only; no C++/torch types.  All functions return 0 (RSX_OK) or a
+ * negative rsx_status; none of them has a CPU fallback -- without a CUDA device they fail
+ * with RSX_ERR_NO_DEVICE / RSX_ERR_CUDA.
+ */
+#ifndef RSX_H
+#define RSX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSX_VERSION 100 /* 0.1.0 */
+
+typedef enum rsx_status {
+	RSX_OK = 0,
+	RSX_ERR_INVALID = -1,     /* bad layout / null pointer / unsupported combination        */
+	RSX_ERR_CUDA = -2,        /* a CUDA runtime call failed (see rsx_last_cuda_error)        */
+	RSX_ERR_NO_DEVICE = -3,   /* no CUDA device: there is no CPU path                         */
+	RSX_ERR_WORKSPACE = -4,   /* caller workspace too small                                   */
+	RSX_ERR_IDX_RANGE = -5,   /* n - 1 does not fit idx_bytes (reference would silently wrap) */
+	RSX_ERR_MIXED_MEMORY = -6 /* src / aux / index_buffer not all host or all device          */
+} rsx_status;
+
+/* How the reference's KeyFunc (radix_sort.hpp:31-35) is expressed across a C ABI.
+ * A device kernel cannot call a host lambda, so the key derivation is described, not passed:
+ *   key      = key_bytes little-endian bytes at key_offset inside a record_bytes-sized record
+ *   derived  = kdf(key), optionally complemented
+ * which covers every KDF the reference ships or documents (radix_sort_basic_kdf.hpp:19-46,
+ * README.md:562-627) and the record lambdas of its tests (radix_tests.cpp:41-43,111-113,175-177). */
+typedef enum rsx_kdf {
+	RSX_KDF_UNSIGNED = 0, /* identity                  radix_sort_basic_kdf.hpp:19-23 */
+	RSX_KDF_SIGNED = 1,   /* key ^ highbit             radix_sort_basic_kdf.hpp:26-30 */
+	RSX_KDF_FLOAT = 2     /* IEEE-754 total-order flip radix_sort_basic_kdf.hpp:32-46 (key_bytes 4 or 8) */
+} rsx_kdf;
+
+#define RSX_FLAG_INVERT 1u /* derived = ~derived: descending order, README.md:564-574 */
+
+typedef struct rsx_layout {
+	uint32_t record_bytes; /* sizeof(T): 1, 2, 4, 8 or 16                                 */
+	uint32_t key_offset;   /* key must lie inside one aligned 8-byte word of the record   */
+	uint32_t key_bytes;    /* sizeof(KeyType) = number of 8-bit columns: 1, 2, 4 or 8      */
+	uint32_t kdf_kind;     /* rsx_kdf                                                      */
+	uint32_t flags;        /* RSX_FLAG_*                                                   */
+} rsx_layout;
+
+/* What the sort found out on the device (read back once, 1 small D2H at the end). */
+typedef struct rsx_report {
+	uint32_t early_exit;   /* n < 2 or input already ordered: nothing was moved (radix_sort.hpp:60-62) */
+	uint32_t ncols;        /* live (non-trivial) 8-bit columns actually sorted (radix_sort.hpp:65-70) */
+	uint32_t live_mask;    /* bit c set <=> column c was live                               */
+	uint32_t result_in_aux;/* 1 <=> result pointer is aux / index_buffer + n (radix_sort.hpp:89-92) */
+	uint32_t kernel_launches; /* kernels launched by this call                             */
+	uint32_t staged;       /* 1 <=> host buffers were staged through device memory         */
+} rsx_report;
+
+/* ---- value sort --------------------------------------------------------------------------
+ * Replaces  T* radix_sort(T* src, T* aux, size_t n, KeyFunc&& kf)      radix_sort.hpp:98-115
+ *      and  rs_sort_main                                               radix_sort.hpp:31-93
+ * src and aux hold n records each, both are clobbered, *result aliases one of them by the
+ * reference's rule: src if the number of live columns is even or on early exit, else aux.
+ * Device (or managed) pointers are sorted in place on the GPU; plain host pointers are
+ * staged H2D -> sort -> D2H into the buffer the reference would have returned.
+ * `stream` is a cudaStream_t (NULL = default stream).  The call is synchronous like the
+ * reference: it returns after the result is complete.  `report` may be NULL. */
+int rsx_sort(void *src, void *aux, size_t n, const rsx_layout *layout, void **result,
+             rsx_report *report, void *stream);
+
+/* ---- rank sort (argsort) -----------------------------------------------------------------
+ * Replaces  IdxType* radix_sort_rank(const T* src, IdxType* index_buffer, size_t n, KeyFunc&&)
+ *                                                                 radix_sort_rank.hpp:97-112
+ *      and  rs_sort_rank                                          radix_sort_rank.hpp:22-92
+ * src is never written.  index_buffer holds 2n entries of idx_bytes (1, 2, 4 or 8) each;
+ * *result = index_buffer or index_buffer + n (same parity rule).  The output is the stable
+ * argsort by derived key -- the semantics the reference documents (README.md:485-490) and
+ * its C listing implements (radix_sort_u32_ranks.c:91-107); the shipped header deviates from
+ * it for >= 2 live columns (radix_sort_rank.hpp:82).  Keys travel beside the
+ * indices in library workspace, so no pass gathers through the index. */
+int rsx_sort_rank(const void *src, void *index_buffer, size_t n, const rsx_layout *layout,
+                  int idx_bytes, void **result, rsx_report *report, void *stream);
+
+/* ---- the two halves of the path, exposed for parity tests and profiling --------------------
+ * rsx_histogram = phase 1-3 of rs_sort_main (radix_sort.hpp:46-80): one read of the keys
+ * producing all key_bytes x 256 digit counts (column-major, BEFORE the exclusive scan, bins
+ * indexed by the DERIVED key's digit), the number of descents (i with kdf(a[i]) > kdf(a[i+1]);
+ * the reference's n_unsorted equals 1 + descents for n >= 1) and the live-column mask.
+ * `src` must be a device pointer; hist_out / descents_out / report are HOST pointers. */
+int rsx_histogram(const void *src, size_t n, const rsx_layout *layout,
+                  uint64_t *hist_out /* key_bytes*256 */, uint64_t *descents_out,
+                  rsx_report *report, void *stream);
+
+/* One stable 8-bit-digit scatter pass (radix_sort.hpp:83-88) on column `col`, device
+ * pointers only, unconditionally (no column skipping).  payload_* may be NULL; otherwise a
+ * payload_bytes (4 or 8) lane is carried with the records. */
+int rsx_scatter_pass(const void *src, void *dst, const void *payload_src, void *payload_dst,
+                     int payload_bytes, size_t n, const rsx_layout *layout, int col, void *stream);
+
+/* ---- workspace ---------------------------------------------------------------------------
+ * The reference allocates nothing (stack histograms).  The device path needs scratch for the
+ * digit histograms, the pass table and the decoupled look-back state, and -- for rank sorts --
+ * key/index ping-pong buffers.  By default it is a grow-only per-device cache owned by the
+ * library; rsx_workspace_bytes lets a caller reserve it up front (rsx_reserve) so that no
+ * cudaMalloc happens inside a timed region. */
+size_t rsx_workspace_bytes(size_t n, const rsx_layout *layout, int rank_idx_bytes /* 0 = value sort */);
+int rsx_reserve(size_t bytes);
+void rsx_release(void);
+
+/* ---- synthetic inputs for the benchmark (not on the sort path) ----------------------------
+ * Device-side twin of keygen.py: dst[i] = ((dist(seed, start + i) & mask) | orv) truncated to
+ * key_bytes, for i in [0, count). */
+int rsx_fill_keys(void *dst, size_t count, int key_bytes, uint64_t seed, uint64_t start,
+                  int dist, uint64_t mask, uint64_t orv, void *stream);
+
+/* Device-side verification for inputs too large for a CPU oracle: number of descents of the
+ * derived key over the array, plus order-independent multiset checksums (sum and xor of
+ * mix64(record's first 8 bytes... of the derived key)).  Outputs are HOST pointers. */
+int rsx_verify(const void *data, size_t n, const rsx_layout *layout, uint64_t *descents_out,
+               uint64_t *sum_out, uint64_t *xor_out, void *stream);
+
+/* ---- misc -------------------------------------------------------------------------------- */
+const char *rsx_strerror(int status);
+const char *rsx_last_cuda_error(void); /* thread-local text of the last failing CUDA call */
+int rsx_version(void);
+uint64_t rsx_total_kernel_launches(void); /* process-wide count, for bench.py's gpu_launches */
+/* Tuning/debug knob: 0 = default.  See DESIGN.md "variants". */
+int rsx_set_option(const char *name, long value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSX_H */

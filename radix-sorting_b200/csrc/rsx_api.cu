@@ -1,0 +1,685 @@
+// rsx_api.cu -- the C ABI (include/rsx.h): argument checking, workspace, pass orchestration.
+//
+// Host-side control flow mirrors rs_sort_main (radix_sort.hpp:31-93) with the data-dependent
+// decisions moved to the device:
+//     memset(workspace head + look-back state)
+//     K1 histogram_kernel      radix_sort.hpp:48-58
+//     K2 setup_kernel          radix_sort.hpp:60-80   (writes the device pass table)
+//     K3 scatter_kernel x wc   radix_sort.hpp:83-90   (trivial columns return at once)
+//     8-byte read-back of {early_exit, ncols} -> which buffer to return (radix_sort.hpp:89-92)
+// There is no CPU implementation anywhere in this file: without a device every entry point
+// fails.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "rsx_scatter.cuh"
+
+namespace rsx {
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+
+thread_local char t_err[512] = "";
+
+int fail_cuda(cudaError_t e, const char *what) {
+	snprintf(t_err, sizeof(t_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+	(void)cudaGetLastError(); // clear the sticky-free error state
+	return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? RSX_ERR_NO_DEVICE : RSX_ERR_CUDA;
+}
+#define CU(call)                                  \
+	do {                                          \
+		cudaError_t e_ = (call);                  \
+		if (e_ != cudaSuccess)                    \
+			return fail_cuda(e_, #call);          \
+	} while (0)
+
+// ---- per-device state: SM count, grow-only workspace, pinned read-back slot -------------------
+struct DeviceState {
+	std::mutex mu;
+	int num_sms = 0;
+	void *ws = nullptr;
+	size_t ws_bytes = 0;
+	bool busy = false;
+	Ctl *pinned = nullptr; // one slot per device is enough: guarded by `busy`
+};
+constexpr int kMaxDevices = 64;
+DeviceState g_dev[kMaxDevices];
+
+int current_device(int *dev) {
+	CU(cudaGetDevice(dev));
+	if (*dev < 0 || *dev >= kMaxDevices)
+		return RSX_ERR_INVALID;
+	DeviceState &D = g_dev[*dev];
+	std::lock_guard<std::mutex> lk(D.mu);
+	if (D.num_sms == 0)
+		CU(cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, *dev));
+	return RSX_OK;
+}
+
+struct Lease {
+	int dev = -1;
+	void *ptr = nullptr;
+	Ctl *pinned = nullptr;
+	bool cached = false;
+	bool own_pinned = false;
+	~Lease() {
+		if (dev < 0)
+			return;
+		if (cached) {
+			std::lock_guard<std::mutex> lk(g_dev[dev].mu);
+			g_dev[dev].busy = false;
+		} else {
+			if (ptr)
+				cudaFree(ptr);
+			if (own_pinned && pinned)
+				cudaFreeHost(pinned);
+		}
+	}
+};
+
+int acquire(Lease &L, int dev, size_t bytes) {
+	DeviceState &D = g_dev[dev];
+	L.dev = dev;
+	std::unique_lock<std::mutex> lk(D.mu);
+	if (!D.busy) {
+		if (D.ws_bytes < bytes) {
+			if (D.ws) {
+				cudaFree(D.ws);
+				D.ws = nullptr;
+				D.ws_bytes = 0;
+			}
+			CU(cudaMalloc(&D.ws, bytes));
+			D.ws_bytes = bytes;
+		}
+		if (!D.pinned)
+			CU(cudaHostAlloc((void **)&D.pinned, sizeof(Ctl), cudaHostAllocDefault));
+		D.busy = true;
+		L.ptr = D.ws;
+		L.pinned = D.pinned;
+		L.cached = true;
+		return RSX_OK;
+	}
+	lk.unlock(); // another host thread is sorting on this device: private scratch for this call
+	CU(cudaMalloc(&L.ptr, bytes));
+	CU(cudaHostAlloc((void **)&L.pinned, sizeof(Ctl), cudaHostAllocDefault));
+	L.own_pinned = true;
+	return RSX_OK;
+}
+
+// ---- layout ---------------------------------------------------------------------------------
+int check_layout(const rsx_layout *L, KeyDesc *kd) {
+	if (!L)
+		return RSX_ERR_INVALID;
+	const uint32_t rb = L->record_bytes, kb = L->key_bytes, ko = L->key_offset;
+	if (!(rb == 1 || rb == 2 || rb == 4 || rb == 8 || rb == 16))
+		return RSX_ERR_INVALID;
+	if (!(kb == 1 || kb == 2 || kb == 4 || kb == 8))
+		return RSX_ERR_INVALID;
+	if (ko + kb > rb || (ko / 8) != ((ko + kb - 1) / 8)) // key inside one aligned 8-byte word
+		return RSX_ERR_INVALID;
+	if (L->kdf_kind > RSX_KDF_FLOAT || (L->flags & ~RSX_FLAG_INVERT))
+		return RSX_ERR_INVALID;
+	if (L->kdf_kind == RSX_KDF_FLOAT && !((kb == 4 || kb == 8) && ko % kb == 0))
+		return RSX_ERR_INVALID;
+	kd->word_sel = ko / 8;
+	kd->key_shift = 8u * (ko % 8);
+	kd->key_bytes = kb;
+	kd->kdf_kind = L->kdf_kind;
+	kd->invert = (L->flags & RSX_FLAG_INVERT) ? 1u : 0u;
+	return RSX_OK;
+}
+
+// Record whose derived key is all ones: pads the last tile so that padding sorts last.
+ulonglong2 pad_record(const KeyDesc &kd) {
+	const unsigned long long m = kd.key_bytes >= 8 ? ~0ULL : ((1ULL << (8 * kd.key_bytes)) - 1ULL);
+	const unsigned long long top = 1ULL << (8 * kd.key_bytes - 1);
+	unsigned long long k = kd.invert ? 0ULL : m; // undo the complement
+	if (kd.kdf_kind == RSX_KDF_SIGNED)
+		k ^= top;
+	else if (kd.kdf_kind == RSX_KDF_FLOAT)
+		k ^= (k & top) ? top : m; // inverse of: sign set -> ^m, sign clear -> ^top
+	ulonglong2 r = make_ulonglong2(0, 0);
+	(kd.word_sel ? r.y : r.x) = k << kd.key_shift;
+	return r;
+}
+
+enum PtrKind { PK_HOST, PK_DEVICE };
+int ptr_kind(const void *p, PtrKind *k) {
+	cudaPointerAttributes a;
+	cudaError_t e = cudaPointerGetAttributes(&a, p);
+	if (e != cudaSuccess)
+		return fail_cuda(e, "cudaPointerGetAttributes");
+	*k = (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? PK_DEVICE : PK_HOST;
+	return RSX_OK;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Plan {
+	KeyDesc kd;
+	uint32_t rb;
+	int pl_bytes;       // payload lane carried by the passes (0, 4, 8)
+	size_t n;
+	PassGeometry geo;
+	uint32_t tiles;
+	bool wide;
+	size_t status_bytes_per_col;
+	size_t off_status, off_rec[2], off_idx[2], total;
+	int n_rec_bufs;
+};
+
+void make_plan(Plan &P, size_t n, const rsx_layout *L, const KeyDesc &kd, int rank_idx_bytes, int forced_pl = -1) {
+	P.kd = kd;
+	P.rb = L->record_bytes;
+	P.n = n;
+	P.pl_bytes = forced_pl >= 0 ? forced_pl : rank_idx_bytes == 0 ? 0 : (rank_idx_bytes == 8 ? 8 : 4);
+	P.geo = scatter_geometry(P.rb, P.pl_bytes);
+	P.tiles = (uint32_t)((n + P.geo.tile - 1) / P.geo.tile);
+	P.wide = n >= (1ULL << 30);
+	P.status_bytes_per_col = (size_t)P.tiles * kBins * (P.wide ? 8 : 4);
+	size_t off = align_up(sizeof(WsHead), 256);
+	P.off_status = off;
+	off += align_up(P.status_bytes_per_col * kd.key_bytes, 256);
+	P.n_rec_bufs = 0;
+	P.off_rec[0] = P.off_rec[1] = P.off_idx[0] = P.off_idx[1] = 0;
+	if (rank_idx_bytes) {
+		// records travel beside the indices; the last live pass writes no records, so at most
+		// min(2, columns - 1) record buffers are ever needed.
+		P.n_rec_bufs = kd.key_bytes >= 3 ? 2 : (int)kd.key_bytes - 1;
+		for (int i = 0; i < P.n_rec_bufs; ++i) {
+			P.off_rec[i] = off;
+			off += align_up(n * P.rb, 256);
+		}
+		if (rank_idx_bytes < 4) {
+			for (int i = 0; i < 2; ++i) {
+				P.off_idx[i] = off;
+				off += align_up(n * 4, 256);
+			}
+		}
+	}
+	P.total = off;
+}
+
+int run_scatter(const PassBuffers &pb, const Plan &P, int col, WsHead *ws, bool forced, void *status,
+                unsigned int *ticket, int num_sms, cudaStream_t st) {
+	CU(launch_scatter(pb, P.n, P.rb, P.pl_bytes, P.kd, col, ws, forced, status, ticket, P.wide, num_sms, st));
+	return RSX_OK;
+}
+
+// Enqueue memset + K1 + K2 (+ passes).  Everything is asynchronous on `st`.
+int enqueue_front(const void *src, const Plan &P, unsigned char *wsp, int num_sms, cudaStream_t st) {
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
+	CU(cudaMemsetAsync(wsp, 0, kWsZeroBytes, st));
+	CU(launch_histogram(src, P.n, P.rb, P.kd, ws, num_sms, st));
+	CU(launch_setup(src, P.n, P.rb, P.kd, ws, st));
+	return RSX_OK;
+}
+
+int enqueue_passes(const PassBuffers &pb, const Plan &P, unsigned char *wsp, int num_sms, cudaStream_t st) {
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
+	CU(cudaMemsetAsync(wsp + P.off_status, 0, P.status_bytes_per_col * P.kd.key_bytes, st));
+	for (uint32_t c = 0; c < P.kd.key_bytes; ++c) {
+		int r = run_scatter(pb, P, (int)c, ws, false, wsp + P.off_status + c * P.status_bytes_per_col,
+		                    &ws->tickets[c], num_sms, st);
+		if (r)
+			return r;
+	}
+	return RSX_OK;
+}
+
+int read_ctl(const unsigned char *wsp, Ctl *pinned, cudaStream_t st, unsigned long long launches0,
+             rsx_report *rep, bool staged) {
+	const WsHead *ws = reinterpret_cast<const WsHead *>(wsp);
+	CU(cudaMemcpyAsync(pinned, &ws->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	if (rep) {
+		rep->early_exit = pinned->early_exit;
+		rep->ncols = pinned->early_exit ? 0 : pinned->ncols;
+		rep->live_mask = pinned->early_exit ? 0 : pinned->live_mask;
+		rep->result_in_aux = pinned->early_exit ? 0 : (pinned->ncols & 1u);
+		rep->kernel_launches = (uint32_t)(g_launches.load() - launches0);
+		rep->staged = staged;
+	}
+	return RSX_OK;
+}
+
+void trivial_report(rsx_report *rep) {
+	if (rep) {
+		memset(rep, 0, sizeof(*rep));
+		rep->early_exit = 1;
+	}
+}
+
+} // namespace
+
+// ---- launch glue declared in rsx_internal.cuh --------------------------------------------------
+PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes) {
+	PassGeometry g{};
+#define GEO(ES, PL)                                                                      \
+	if (record_bytes == ES && payload_bytes == PL) {                                     \
+		g.threads = ScatterCfg<ES, PL>::kThreads;                                        \
+		g.items = ScatterCfg<ES, PL>::kItems;                                            \
+		g.smem_bytes = ScatterSmem<ES, PL, ScatterCfg<ES, PL>::kThreads, ScatterCfg<ES, PL>::kItems>::kBytes; \
+	}
+	GEO(1, 0) GEO(1, 4) GEO(1, 8) GEO(2, 0) GEO(2, 4) GEO(2, 8) GEO(4, 0) GEO(4, 4) GEO(4, 8)
+	GEO(8, 0) GEO(8, 4) GEO(8, 8) GEO(16, 0) GEO(16, 4) GEO(16, 8)
+#undef GEO
+	g.tile = g.threads * g.items;
+	g.ctas_per_sm = 0;
+	return g;
+}
+
+cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_bytes, int payload_bytes,
+                           const KeyDesc &kd, int col, const WsHead *ws, bool forced, void *status,
+                           unsigned int *ticket, bool wide, int num_sms, cudaStream_t st) {
+	ScatterParams sp;
+	sp.pb = pb;
+	sp.n = n;
+	const PassGeometry g = scatter_geometry(record_bytes, payload_bytes);
+	if (g.tile == 0)
+		return cudaErrorInvalidValue;
+	sp.num_tiles = (uint32_t)((n + g.tile - 1) / g.tile);
+	sp.col = (uint32_t)col;
+	sp.dd = make_digit_desc(kd, col);
+	sp.offs = ws->offs + (size_t)col * kBins;
+	sp.ctl = forced ? nullptr : &ws->ctl;
+	sp.status = status;
+	sp.ticket = ticket;
+	sp.pad_rec = pad_record(kd);
+	const bool is_float = kd.kdf_kind == RSX_KDF_FLOAT;
+	switch (record_bytes) {
+	case 1: return launch_scatter_1(sp, payload_bytes, is_float, wide, num_sms, st);
+	case 2: return launch_scatter_2(sp, payload_bytes, is_float, wide, num_sms, st);
+	case 4: return launch_scatter_4(sp, payload_bytes, is_float, wide, num_sms, st);
+	case 8: return launch_scatter_8(sp, payload_bytes, is_float, wide, num_sms, st);
+	case 16: return launch_scatter_16(sp, payload_bytes, is_float, wide, num_sms, st);
+	}
+	return cudaErrorInvalidValue;
+}
+
+} // namespace rsx
+
+using namespace rsx;
+
+// ================================================================================================
+extern "C" {
+
+int rsx_version(void) { return RSX_VERSION; }
+
+const char *rsx_strerror(int s) {
+	switch (s) {
+	case RSX_OK: return "ok";
+	case RSX_ERR_INVALID: return "invalid argument or unsupported record layout";
+	case RSX_ERR_CUDA: return "CUDA error (see rsx_last_cuda_error)";
+	case RSX_ERR_NO_DEVICE: return "no CUDA device (librsx has no CPU path)";
+	case RSX_ERR_WORKSPACE: return "workspace too small";
+	case RSX_ERR_IDX_RANGE: return "n - 1 does not fit the index type";
+	case RSX_ERR_MIXED_MEMORY: return "buffers must be all host or all device memory";
+	}
+	return "unknown status";
+}
+
+const char *rsx_last_cuda_error(void) { return t_err; }
+
+uint64_t rsx_total_kernel_launches(void) { return g_launches.load(); }
+
+int rsx_set_option(const char *name, long value) {
+	(void)name;
+	(void)value;
+	return RSX_ERR_INVALID; // no tunables in this build
+}
+
+size_t rsx_workspace_bytes(size_t n, const rsx_layout *layout, int rank_idx_bytes) {
+	KeyDesc kd;
+	if (check_layout(layout, &kd) != RSX_OK)
+		return 0;
+	Plan P;
+	make_plan(P, n < 2 ? 2 : n, layout, kd, rank_idx_bytes);
+	return P.total;
+}
+
+int rsx_reserve(size_t bytes) {
+	int dev;
+	int r = current_device(&dev);
+	if (r)
+		return r;
+	Lease L;
+	return acquire(L, dev, bytes);
+}
+
+void rsx_release(void) {
+	int dev;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices)
+		return;
+	DeviceState &D = g_dev[dev];
+	std::lock_guard<std::mutex> lk(D.mu);
+	if (!D.busy && D.ws) {
+		cudaFree(D.ws);
+		D.ws = nullptr;
+		D.ws_bytes = 0;
+	}
+}
+
+// ---- value sort --------------------------------------------------------------------------------
+static int sort_device(void *src, void *aux, size_t n, const rsx_layout *layout, const KeyDesc &kd,
+                       void **result, rsx_report *rep, cudaStream_t st, int dev, bool staged) {
+	const unsigned long long l0 = g_launches.load();
+	Plan P;
+	make_plan(P, n, layout, kd, 0);
+	Lease L;
+	int r = acquire(L, dev, P.total);
+	if (r)
+		return r;
+	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
+	const int sms = g_dev[dev].num_sms;
+	if ((r = enqueue_front(src, P, wsp, sms, st)))
+		return r;
+	PassBuffers pb{};
+	pb.rec_first = src;
+	pb.rec_buf[0] = aux; // pass 0: src -> aux, pass 1: aux -> src, ... (radix_sort.hpp:89)
+	pb.rec_buf[1] = src;
+	if ((r = enqueue_passes(pb, P, wsp, sms, st)))
+		return r;
+	rsx_report local;
+	if (!rep)
+		rep = &local;
+	if ((r = read_ctl(wsp, L.pinned, st, l0, rep, staged)))
+		return r;
+	*result = rep->result_in_aux ? aux : src;
+	return RSX_OK;
+}
+
+int rsx_sort(void *src, void *aux, size_t n, const rsx_layout *layout, void **result, rsx_report *rep,
+             void *stream) {
+	KeyDesc kd;
+	int r = check_layout(layout, &kd);
+	if (r)
+		return r;
+	if (!result || (n && (!src || !aux)))
+		return RSX_ERR_INVALID;
+	if (n < 2) { // radix_sort.hpp:100-101
+		*result = src;
+		trivial_report(rep);
+		return RSX_OK;
+	}
+	int dev;
+	if ((r = current_device(&dev)))
+		return r;
+	PtrKind ks, ka;
+	if ((r = ptr_kind(src, &ks)) || (r = ptr_kind(aux, &ka)))
+		return r;
+	if (ks != ka)
+		return RSX_ERR_MIXED_MEMORY;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if (ks == PK_DEVICE)
+		return sort_device(src, aux, n, layout, kd, result, rep, st, dev, false);
+
+	// Host buffers: stage through device memory.  The reference sorts host memory in place;
+	// the bytes land in the buffer it would have returned, the other buffer is left as is
+	// (the reference leaves the penultimate pass there, which callers must treat as garbage).
+	const size_t bytes = n * layout->record_bytes;
+	void *d = nullptr;
+	CU(cudaMalloc(&d, 2 * align_up(bytes, 256)));
+	void *dsrc = d, *daux = static_cast<unsigned char *>(d) + align_up(bytes, 256);
+	void *dres = nullptr;
+	rsx_report local;
+	if (!rep)
+		rep = &local;
+	r = RSX_OK;
+	cudaError_t e = cudaMemcpyAsync(dsrc, src, bytes, cudaMemcpyHostToDevice, st);
+	if (e != cudaSuccess)
+		r = fail_cuda(e, "H2D");
+	if (!r)
+		r = sort_device(dsrc, daux, n, layout, kd, &dres, rep, st, dev, true);
+	if (!r && !rep->early_exit) {
+		void *hres = rep->result_in_aux ? aux : src;
+		e = cudaMemcpyAsync(hres, dres, bytes, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(st);
+		if (e != cudaSuccess)
+			r = fail_cuda(e, "D2H");
+	}
+	if (!r)
+		*result = rep->result_in_aux ? aux : src;
+	cudaFree(d);
+	return r;
+}
+
+// ---- rank sort ---------------------------------------------------------------------------------
+static int rank_device(const void *src, void *ib, size_t n, const rsx_layout *layout, const KeyDesc &kd,
+                       int idx_bytes, void **result, rsx_report *rep, cudaStream_t st, int dev, bool staged) {
+	const unsigned long long l0 = g_launches.load();
+	Plan P;
+	make_plan(P, n, layout, kd, idx_bytes);
+	Lease L;
+	int r = acquire(L, dev, P.total);
+	if (r)
+		return r;
+	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
+	const int sms = g_dev[dev].num_sms;
+	if ((r = enqueue_front(src, P, wsp, sms, st)))
+		return r;
+	CU(launch_iota_if_early(ib, idx_bytes, n, &ws->ctl, st)); // radix_sort_rank.hpp:52-57
+	unsigned char *ibb = static_cast<unsigned char *>(ib);
+	PassBuffers pb{};
+	pb.rec_first = src;
+	pb.rec_buf[0] = P.n_rec_bufs > 0 ? wsp + P.off_rec[0] : nullptr;
+	pb.rec_buf[1] = P.n_rec_bufs > 1 ? wsp + P.off_rec[1] : pb.rec_buf[0];
+	pb.pl_first = nullptr;
+	pb.synth_index = 1;   // radix_sort_rank.hpp:52: index_buffer[i] = i, never materialised
+	pb.skip_last_rec = 1;
+	if (idx_bytes >= 4) {
+		pb.pl_buf[0] = ibb + n * (size_t)idx_bytes; // radix_sort_rank.hpp:77-78: first pass writes the 2nd half
+		pb.pl_buf[1] = ibb;
+	} else {
+		pb.pl_buf[0] = wsp + P.off_idx[0];
+		pb.pl_buf[1] = wsp + P.off_idx[1];
+	}
+	if ((r = enqueue_passes(pb, P, wsp, sms, st)))
+		return r;
+	if (idx_bytes < 4)
+		CU(launch_narrow_index(reinterpret_cast<uint32_t *>(wsp + P.off_idx[0]),
+		                       reinterpret_cast<uint32_t *>(wsp + P.off_idx[1]), ib, idx_bytes, n, &ws->ctl, st));
+	rsx_report local;
+	if (!rep)
+		rep = &local;
+	if ((r = read_ctl(wsp, L.pinned, st, l0, rep, staged)))
+		return r;
+	*result = rep->result_in_aux ? ibb + n * (size_t)idx_bytes : ibb; // radix_sort_rank.hpp:91
+	return RSX_OK;
+}
+
+int rsx_sort_rank(const void *src, void *index_buffer, size_t n, const rsx_layout *layout, int idx_bytes,
+                  void **result, rsx_report *rep, void *stream) {
+	KeyDesc kd;
+	int r = check_layout(layout, &kd);
+	if (r)
+		return r;
+	if (!(idx_bytes == 1 || idx_bytes == 2 || idx_bytes == 4 || idx_bytes == 8))
+		return RSX_ERR_INVALID;
+	if (!result || (n && (!src || !index_buffer)))
+		return RSX_ERR_INVALID;
+	if (idx_bytes < 8 && n && (n - 1) >> (8 * idx_bytes))
+		return RSX_ERR_IDX_RANGE;
+	int dev;
+	if (n < 2) { // radix_sort_rank.hpp:28-32
+		if (n == 1) {
+			PtrKind k;
+			if ((r = current_device(&dev)) || (r = ptr_kind(index_buffer, &k)))
+				return r;
+			if (k == PK_DEVICE)
+				CU(cudaMemset(index_buffer, 0, idx_bytes));
+			else
+				memset(index_buffer, 0, idx_bytes);
+		}
+		*result = index_buffer;
+		trivial_report(rep);
+		return RSX_OK;
+	}
+	if ((r = current_device(&dev)))
+		return r;
+	PtrKind ks, ki;
+	if ((r = ptr_kind(src, &ks)) || (r = ptr_kind(index_buffer, &ki)))
+		return r;
+	if (ks != ki)
+		return RSX_ERR_MIXED_MEMORY;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if (ks == PK_DEVICE)
+		return rank_device(src, index_buffer, n, layout, kd, idx_bytes, result, rep, st, dev, false);
+
+	const size_t sbytes = n * layout->record_bytes, ibytes = n * (size_t)idx_bytes;
+	void *d = nullptr;
+	CU(cudaMalloc(&d, align_up(sbytes, 256) + 2 * ibytes));
+	unsigned char *dsrc = static_cast<unsigned char *>(d), *dib = dsrc + align_up(sbytes, 256);
+	void *dres = nullptr;
+	rsx_report local;
+	if (!rep)
+		rep = &local;
+	r = RSX_OK;
+	cudaError_t e = cudaMemcpyAsync(dsrc, src, sbytes, cudaMemcpyHostToDevice, st);
+	if (e != cudaSuccess)
+		r = fail_cuda(e, "H2D");
+	if (!r)
+		r = rank_device(dsrc, dib, n, layout, kd, idx_bytes, &dres, rep, st, dev, true);
+	unsigned char *hres = static_cast<unsigned char *>(index_buffer);
+	if (!r) {
+		hres += rep->result_in_aux ? ibytes : 0;
+		e = cudaMemcpyAsync(hres, dres, ibytes, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(st);
+		if (e != cudaSuccess)
+			r = fail_cuda(e, "D2H");
+	}
+	if (!r)
+		*result = hres;
+	cudaFree(d);
+	return r;
+}
+
+// ---- halves of the path, for parity tests and profiling ------------------------------------------
+int rsx_histogram(const void *src, size_t n, const rsx_layout *layout, uint64_t *hist_out,
+                  uint64_t *descents_out, rsx_report *rep, void *stream) {
+	KeyDesc kd;
+	int r = check_layout(layout, &kd);
+	if (r)
+		return r;
+	if (!src || n < 2)
+		return RSX_ERR_INVALID;
+	int dev;
+	if ((r = current_device(&dev)))
+		return r;
+	PtrKind k;
+	if ((r = ptr_kind(src, &k)))
+		return r;
+	if (k != PK_DEVICE)
+		return RSX_ERR_MIXED_MEMORY;
+	const unsigned long long l0 = g_launches.load();
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	Plan P;
+	make_plan(P, n, layout, kd, 0);
+	Lease L;
+	if ((r = acquire(L, dev, P.total)))
+		return r;
+	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
+	if ((r = enqueue_front(src, P, wsp, g_dev[dev].num_sms, st)))
+		return r;
+	rsx_report local;
+	if (!rep)
+		rep = &local;
+	if ((r = read_ctl(wsp, L.pinned, st, l0, rep, false)))
+		return r;
+	rep->live_mask = L.pinned->live_mask; // report the probe even when the input is presorted
+	rep->ncols = L.pinned->ncols;
+	if (hist_out)
+		CU(cudaMemcpy(hist_out, ws->hist, sizeof(uint64_t) * kBins * kd.key_bytes, cudaMemcpyDeviceToHost));
+	if (descents_out)
+		CU(cudaMemcpy(descents_out, &ws->descents, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+	return RSX_OK;
+}
+
+int rsx_scatter_pass(const void *src, void *dst, const void *payload_src, void *payload_dst,
+                     int payload_bytes, size_t n, const rsx_layout *layout, int col, void *stream) {
+	KeyDesc kd;
+	int r = check_layout(layout, &kd);
+	if (r)
+		return r;
+	if (!src || !dst || n < 1 || col < 0 || col >= (int)kd.key_bytes)
+		return RSX_ERR_INVALID;
+	if (!(payload_bytes == 0 || payload_bytes == 4 || payload_bytes == 8))
+		return RSX_ERR_INVALID;
+	if (payload_bytes && (!payload_src || !payload_dst))
+		return RSX_ERR_INVALID;
+	int dev;
+	if ((r = current_device(&dev)))
+		return r;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	Plan P;
+	make_plan(P, n, layout, kd, 0, payload_bytes);
+	Lease L;
+	if ((r = acquire(L, dev, P.total)))
+		return r;
+	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
+	const int sms = g_dev[dev].num_sms;
+	if ((r = enqueue_front(src, P, wsp, sms, st))) // histogram + scan give this column's offsets
+		return r;
+	CU(cudaMemsetAsync(wsp + P.off_status, 0, P.status_bytes_per_col, st));
+	PassBuffers pb{};
+	pb.rec_first = src;
+	pb.rec_buf[0] = dst;
+	pb.rec_buf[1] = dst;
+	pb.pl_first = payload_src;
+	pb.pl_buf[0] = payload_dst;
+	pb.pl_buf[1] = payload_dst;
+	if ((r = run_scatter(pb, P, col, ws, true, wsp + P.off_status, &ws->tickets[col], sms, st)))
+		return r;
+	CU(cudaStreamSynchronize(st));
+	return RSX_OK;
+}
+
+// ---- bench helpers ---------------------------------------------------------------------------------
+int rsx_fill_keys(void *dst, size_t count, int key_bytes, uint64_t seed, uint64_t start, int dist,
+                  uint64_t mask, uint64_t orv, void *stream) {
+	if (!dst && count)
+		return RSX_ERR_INVALID;
+	if (count == 0)
+		return RSX_OK;
+	CU(launch_fill(dst, count, key_bytes, seed, start, dist, mask, orv, static_cast<cudaStream_t>(stream)));
+	return RSX_OK;
+}
+
+int rsx_verify(const void *data, size_t n, const rsx_layout *layout, uint64_t *descents_out,
+               uint64_t *sum_out, uint64_t *xor_out, void *stream) {
+	KeyDesc kd;
+	int r = check_layout(layout, &kd);
+	if (r)
+		return r;
+	int dev;
+	if ((r = current_device(&dev)))
+		return r;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	unsigned long long *d3 = nullptr, h3[3] = {0, 0, 0};
+	CU(cudaMalloc((void **)&d3, 3 * sizeof(unsigned long long)));
+	cudaError_t e = cudaMemsetAsync(d3, 0, 3 * sizeof(unsigned long long), st);
+	if (e == cudaSuccess && n)
+		e = launch_verify(data, n, layout->record_bytes, kd, d3, g_dev[dev].num_sms, st);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(h3, d3, sizeof(h3), cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(st);
+	cudaFree(d3);
+	if (e != cudaSuccess)
+		return fail_cuda(e, "rsx_verify");
+	if (descents_out) *descents_out = h3[0];
+	if (sum_out) *sum_out = h3[1];
+	if (xor_out) *xor_out = h3[2];
+	return RSX_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,289 @@
+// rsx_hist.cu -- K1 fused upfront histogram + K2 setup.
+//
+// K1 replaces the reference's histogram loop (radix_sort.hpp:48-58, radix_sort_rank.hpp:42-53):
+// ONE read of the records produces every column's 256-bin digit histogram and the pre-sorted
+// verdict.  K2 replaces radix_sort.hpp:60-80: early-exit test, trivial-column probe with the
+// first key, exclusive scans -- all on the device, so the host never waits to learn `cols[]`.
+//
+// K1 design (HBM-bound: algorithmic bytes = n * record_bytes, read once):
+//   * 128-bit coalesced loads, 4 in flight per thread, 1024 threads per CTA, one CTA per SM.
+//   * Shared-memory histograms are LANE-PRIVATE: counter (column c, digit d) has 32 copies, one
+//     per lane id, laid out so that copy l lives in bank l.  A warp's 32 increments therefore
+//     never collide in a bank, whatever the digit distribution (a constant column -- the
+//     worst case for a shared counter -- is as fast as a uniform one), and no per-key
+//     warp-match is needed: the warp-level aggregation happens once per flush, when the 32
+//     copies of a bin are summed with a warp reduction and added to the global histogram with
+//     one 64-bit atomic per bin.
+//   * <= 4 columns: 32-bit copies (4 x 256 x 32 x 4 B = 128 KiB).  8 columns: 16-bit copies
+//     packed two per word (128 KiB), flushed before a copy can reach 65535.
+//   * descents (kdf(a[i]) > kdf(a[i+1])) are counted on the fly: inside a thread's vector,
+//     across lanes with a shuffle, across warps with one extra scalar load by lane 31.
+#include "rsx_device.cuh"
+
+namespace rsx {
+
+namespace {
+
+constexpr int kHistThreads = 1024;
+constexpr int kHistUnroll = 4;
+
+template <int KB> struct HistSmem {
+	static constexpr bool kPacked = KB > 4;
+	static constexpr int kWords = KB * kBins * (kPacked ? 16 : 32);
+	static constexpr size_t kBytes = (size_t)kWords * 4;
+};
+
+template <int KB>
+__device__ __forceinline__ void hist_add(uint32_t *sh, uint32_t col, uint32_t digit, uint32_t lane) {
+	if constexpr (HistSmem<KB>::kPacked) {
+		// copy l and copy l+16 share a word (low / high half); word -> bank (d&1)*16 + l%16
+		atomicAdd(&sh[(col * kBins + digit) * 16u + (lane & 15u)], 1u << (lane & 16u));
+	} else {
+		atomicAdd(&sh[(col * kBins + digit) * 32u + lane], 1u);
+	}
+}
+
+// Sum the 32 lane-private copies of every bin, add to the global histogram, zero the copies.
+template <int KB>
+__device__ __forceinline__ void hist_flush(uint32_t *sh, unsigned long long *ghist) {
+	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	for (uint32_t bin = warp; bin < KB * kBins; bin += nwarps) {
+		uint32_t v;
+		if constexpr (HistSmem<KB>::kPacked) {
+			uint32_t w = 0;
+			if (lane < 16) {
+				w = sh[bin * 16u + lane];
+				sh[bin * 16u + lane] = 0;
+			}
+			v = (w & 0xFFFFu) + (w >> 16);
+		} else {
+			v = sh[bin * 32u + lane];
+			sh[bin * 32u + lane] = 0;
+		}
+		v = __reduce_add_sync(0xFFFFFFFFu, v);
+		if (lane == 0 && v)
+			atomicAdd(&ghist[bin], (unsigned long long)v);
+	}
+}
+
+template <int ES, int KB>
+__device__ __forceinline__ void hist_one(uint32_t *sh, unsigned long long key, uint32_t lane) {
+#pragma unroll
+	for (int c = 0; c < KB; ++c)
+		hist_add<KB>(sh, c, (uint32_t)(key >> (8 * c)) & 0xFFu, lane);
+}
+
+template <int ES, int KB>
+__global__ void __launch_bounds__(kHistThreads, 1)
+histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_t head,
+                 size_t n_vec, KeyDesc kd, unsigned long long *__restrict__ ghist,
+                 unsigned long long *__restrict__ gdescents) {
+	using R = typename Rec<ES>::type;
+	constexpr int VEC = 16 / ES;
+	extern __shared__ __align__(16) uint32_t sh[];
+	__shared__ uint32_t s_desc;
+
+	const uint32_t tid = threadIdx.x, lane = tid & 31u;
+	for (int i = tid; i < HistSmem<KB>::kWords; i += kHistThreads)
+		sh[i] = 0;
+	if (tid == 0)
+		s_desc = 0;
+	__syncthreads();
+
+	uint32_t descents = 0;
+	const uint4 *vsrc = reinterpret_cast<const uint4 *>(src + head);
+	const size_t stride = (size_t)gridDim.x * kHistThreads;
+	// CTA-uniform trip count so that the flush barrier is reached by every thread.
+	const size_t per_iter = stride * kHistUnroll;
+	const size_t iters = (n_vec + per_iter - 1) / per_iter;
+	// packed 16-bit copies: a lane copy gains at most (warps * VEC * unroll) per iteration
+	constexpr uint32_t kFlushEvery =
+		HistSmem<KB>::kPacked ? 65535u / ((kHistThreads / 32) * VEC * kHistUnroll) : 0xFFFFFFFFu;
+	uint32_t since_flush = 0;
+
+	for (size_t it = 0; it < iters; ++it) {
+		const size_t v0 = it * per_iter + (size_t)blockIdx.x * kHistThreads + tid;
+		uint4 q[kHistUnroll];
+#pragma unroll
+		for (int u = 0; u < kHistUnroll; ++u) {
+			const size_t v = v0 + (size_t)u * stride;
+			q[u] = v < n_vec ? __ldg(vsrc + v) : make_uint4(0, 0, 0, 0);
+		}
+#pragma unroll
+		for (int u = 0; u < kHistUnroll; ++u) {
+			const size_t v = v0 + (size_t)u * stride;
+			const bool live = v < n_vec;
+			unsigned long long k[VEC];
+			const R *e = reinterpret_cast<const R *>(&q[u]);
+#pragma unroll
+			for (int j = 0; j < VEC; ++j)
+				k[j] = derive_key(key_word<ES>(e[j], kd.word_sel), kd);
+			// successor of this vector's last record: next lane's first key, or a scalar load
+			unsigned long long nxt = __shfl_down_sync(0xFFFFFFFFu, k[0], 1);
+			const size_t next_idx = head + (v + 1) * VEC;
+			bool have_next = live && next_idx < n;
+			if ((lane == 31 || v + 1 >= n_vec) && have_next)
+				nxt = derive_key(key_word<ES>(src[next_idx], kd.word_sel), kd);
+			if (live) {
+#pragma unroll
+				for (int j = 0; j < VEC; ++j)
+					hist_one<ES, KB>(sh, k[j], lane);
+#pragma unroll
+				for (int j = 0; j + 1 < VEC; ++j)
+					descents += k[j] > k[j + 1];
+				if (have_next)
+					descents += k[VEC - 1] > nxt;
+			}
+		}
+		if constexpr (HistSmem<KB>::kPacked) {
+			if (++since_flush == kFlushEvery) {
+				__syncthreads();
+				hist_flush<KB>(sh, ghist);
+				__syncthreads();
+				since_flush = 0;
+			}
+		}
+	}
+
+	// unaligned head and the tail that does not fill a vector: CTA 0, one record per thread
+	if (blockIdx.x == 0) {
+		const size_t tail0 = head + n_vec * VEC;
+		const size_t extra = head + (n - tail0);
+		for (size_t t = tid; t < extra; t += kHistThreads) {
+			const size_t i = t < head ? t : tail0 + (t - head);
+			const unsigned long long k = derive_key(key_word<ES>(src[i], kd.word_sel), kd);
+			hist_one<ES, KB>(sh, k, lane);
+			if (i + 1 < n)
+				descents += k > derive_key(key_word<ES>(src[i + 1], kd.word_sel), kd);
+		}
+	}
+
+	descents = __reduce_add_sync(0xFFFFFFFFu, descents);
+	if (lane == 0 && descents)
+		atomicAdd(&s_desc, descents);
+	__syncthreads();
+	hist_flush<KB>(sh, ghist);
+	if (tid == 0 && s_desc)
+		atomicAdd(gdescents, (unsigned long long)s_desc);
+}
+
+// K2: one CTA, 256 threads; thread d owns bin d of every column.
+template <int ES>
+__global__ void __launch_bounds__(kBins, 1)
+setup_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, KeyDesc kd, WsHead *ws) {
+	__shared__ unsigned long long s_warp[8];
+	__shared__ uint32_t s_live[kMaxCols];
+	const uint32_t d = threadIdx.x, lane = d & 31u, warp = d >> 5;
+	// radix_sort.hpp:65: sample the first key
+	const unsigned long long key0 = derive_key(key_word<ES>(src[0], kd.word_sel), kd);
+	if (d < kd.key_bytes)
+		s_live[d] = ws->hist[d * kBins + ((key0 >> (8 * d)) & 0xFFu)] != n; // radix_sort.hpp:66-69
+	__syncthreads();
+	for (uint32_t c = 0; c < kd.key_bytes; ++c) {
+		// exclusive scan of column c (radix_sort.hpp:73-80); computed for every column, only the
+		// live ones are consumed.
+		const unsigned long long v = ws->hist[c * kBins + d];
+		unsigned long long x = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+			if (lane >= o)
+				x += y;
+		}
+		if (lane == 31)
+			s_warp[warp] = x;
+		__syncthreads();
+		unsigned long long base = 0;
+		for (uint32_t w = 0; w < warp; ++w)
+			base += s_warp[w];
+		ws->offs[c * kBins + d] = base + x - v;
+		__syncthreads();
+	}
+	if (d == 0) {
+		Ctl ctl;
+		ctl.early_exit = ws->descents == 0; // <=> n_unsorted < 2, radix_sort.hpp:60-62
+		ctl.ncols = 0;
+		ctl.live_mask = 0;
+		for (uint32_t c = 0; c < kMaxCols; ++c) {
+			ctl.ordinal[c] = ctl.ncols;
+			if (c < kd.key_bytes && s_live[c]) {
+				ctl.live_mask |= 1u << c;
+				++ctl.ncols;
+			}
+		}
+		ctl.pad = 0;
+		ctl.n = n;
+		ws->ctl = ctl;
+	}
+}
+
+template <int ES, int KB>
+cudaError_t launch_hist_t(const void *src, size_t n, const KeyDesc &kd, WsHead *ws, int num_sms,
+                          cudaStream_t st) {
+	using R = typename Rec<ES>::type;
+	constexpr int VEC = 16 / ES;
+	auto kern = histogram_kernel<ES, KB>;
+	static bool configured[64] = {}; // per device; benign race: setting the attribute is idempotent
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (!configured[dev & 63]) {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                                     (int)HistSmem<KB>::kBytes);
+		if (e != cudaSuccess)
+			return e;
+		configured[dev & 63] = true;
+	}
+	const uintptr_t addr = reinterpret_cast<uintptr_t>(src);
+	size_t head = ((16 - (addr & 15)) & 15) / ES;
+	if (head > n)
+		head = n;
+	const size_t n_vec = (n - head) / VEC;
+	size_t want = (n_vec + (size_t)kHistThreads * kHistUnroll - 1) / ((size_t)kHistThreads * kHistUnroll);
+	int grid = (int)(want < (size_t)num_sms ? (want ? want : 1) : (size_t)num_sms);
+	kern<<<grid, kHistThreads, HistSmem<KB>::kBytes, st>>>(static_cast<const R *>(src), n, head, n_vec,
+	                                                      kd, ws->hist, &ws->descents);
+	count_launch();
+	return cudaGetLastError();
+}
+
+template <int ES>
+cudaError_t launch_hist_es(const void *src, size_t n, const KeyDesc &kd, WsHead *ws, int num_sms,
+                           cudaStream_t st) {
+	switch (kd.key_bytes) {
+	case 1: return launch_hist_t<ES, 1>(src, n, kd, ws, num_sms, st);
+	case 2: if constexpr (ES >= 2) return launch_hist_t<ES, 2>(src, n, kd, ws, num_sms, st); break;
+	case 4: if constexpr (ES >= 4) return launch_hist_t<ES, 4>(src, n, kd, ws, num_sms, st); break;
+	case 8: if constexpr (ES >= 8) return launch_hist_t<ES, 8>(src, n, kd, ws, num_sms, st); break;
+	}
+	return cudaErrorInvalidValue;
+}
+
+} // namespace
+
+cudaError_t launch_histogram(const void *src, size_t n, uint32_t record_bytes, const KeyDesc &kd,
+                             WsHead *ws, int num_sms, cudaStream_t st) {
+	switch (record_bytes) {
+	case 1: return launch_hist_es<1>(src, n, kd, ws, num_sms, st);
+	case 2: return launch_hist_es<2>(src, n, kd, ws, num_sms, st);
+	case 4: return launch_hist_es<4>(src, n, kd, ws, num_sms, st);
+	case 8: return launch_hist_es<8>(src, n, kd, ws, num_sms, st);
+	case 16: return launch_hist_es<16>(src, n, kd, ws, num_sms, st);
+	}
+	return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_setup(const void *src, size_t n, uint32_t record_bytes, const KeyDesc &kd,
+                         WsHead *ws, cudaStream_t st) {
+	switch (record_bytes) {
+	case 1: setup_kernel<1><<<1, kBins, 0, st>>>(static_cast<const uint8_t *>(src), n, kd, ws); break;
+	case 2: setup_kernel<2><<<1, kBins, 0, st>>>(static_cast<const uint16_t *>(src), n, kd, ws); break;
+	case 4: setup_kernel<4><<<1, kBins, 0, st>>>(static_cast<const uint32_t *>(src), n, kd, ws); break;
+	case 8: setup_kernel<8><<<1, kBins, 0, st>>>(static_cast<const unsigned long long *>(src), n, kd, ws); break;
+	case 16: setup_kernel<16><<<1, kBins, 0, st>>>(static_cast<const ulonglong2 *>(src), n, kd, ws); break;
+	default: return cudaErrorInvalidValue;
+	}
+	count_launch();
+	return cudaGetLastError();
+}
+
+} // namespace rsx

@@ -1,0 +1,9 @@
+// rsx_scatter_16.cu -- scatter-pass instantiations for 16-byte records (see rsx_scatter.cuh).
+#include "rsx_scatter.cuh"
+
+namespace rsx {
+cudaError_t launch_scatter_16(const ScatterParams &sp, int payload_bytes, bool is_float, bool wide,
+                          int num_sms, cudaStream_t st) {
+	return launch_scatter_es<16>(sp, payload_bytes, is_float, wide, num_sms, st);
+}
+} // namespace rsx

@@ -1,0 +1,155 @@
+// rsx_util.cu -- small kernels around the hot path: rank-sort index fix-ups, the seeded key
+// generator (device twin of keygen.py) and the on-device verifier used at sizes no CPU oracle
+// can hold.
+#include "rsx_device.cuh"
+
+namespace rsx {
+
+namespace {
+
+// radix_sort_rank.hpp:52-57: on early exit the reference returns the identity permutation in
+// the first half of index_buffer.  The host cannot know about the early exit before the
+// passes are enqueued, so this kernel checks the device pass table itself.
+template <typename I>
+__global__ void iota_if_early_kernel(I *ib, size_t n, const Ctl *ctl) {
+	if (!ctl->early_exit)
+		return;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		ib[i] = (I)i;
+}
+
+// 1- and 2-byte IdxType (radix_tests.cpp:75 sorts with uint8_t indices): the passes carry
+// 32-bit indices in workspace, this narrows them into the half the parity rule designates.
+template <typename I>
+__global__ void narrow_index_kernel(const uint32_t *w0, const uint32_t *w1, I *ib, size_t n, const Ctl *ctl) {
+	if (ctl->early_exit)
+		return; // identity already written by iota_if_early_kernel
+	const uint32_t ncols = ctl->ncols;
+	if (ncols == 0)
+		return;
+	// pass j writes pl_buf[j & 1]; the last live pass is j = ncols - 1
+	const uint32_t *from = ((ncols - 1) & 1u) ? w1 : w0;
+	I *to = (ncols & 1u) ? ib + n : ib;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		to[i] = (I)from[i];
+}
+
+__device__ __forceinline__ unsigned long long stream_word(unsigned long long seed, unsigned long long i, unsigned long long stream) {
+	const unsigned long long base = (seed + 0x632BE59BD9B4E019ULL * stream) * 0x9E3779B97F4A7C15ULL;
+	return mix64(base + i);
+}
+
+template <typename K>
+__global__ void fill_kernel(K *dst, size_t count, unsigned long long seed, unsigned long long start,
+                            int dist, unsigned long long mask, unsigned long long orv) {
+	for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (size_t)gridDim.x * blockDim.x) {
+		const unsigned long long i = start + t;
+		unsigned long long x;
+		switch (dist) {
+		case 0: x = stream_word(seed, i, 0); break;
+		case 1: case 2: case 3:
+			x = stream_word(seed, i, 0);
+			for (int s = 1; s <= dist; ++s)
+				x &= stream_word(seed, i, s);
+			break;
+		case 4: {
+			const unsigned long long hi = stream_word(seed, i, 0) >> 32;
+			const unsigned long long e = hi >> 27, f = hi & ((1ULL << 27) - 1);
+			x = (((1ULL << 27) + f) << e) >> 27;
+			break;
+		}
+		case 5: x = i; break;
+		case 6: x = ~0ULL - i; break;
+		default: x = stream_word(seed, 0, 0); break;
+		}
+		dst[t] = (K)((x & mask) | orv);
+	}
+}
+
+template <int ES>
+__global__ void verify_kernel(const typename Rec<ES>::type *__restrict__ data, size_t n, KeyDesc kd,
+                              unsigned long long *out3) {
+	unsigned long long desc = 0, sum = 0, x = 0;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const unsigned long long k = derive_key(key_word<ES>(data[i], kd.word_sel), kd);
+		if (i + 1 < n)
+			desc += k > derive_key(key_word<ES>(data[i + 1], kd.word_sel), kd);
+		const unsigned long long h = mix64(k + 0x9E3779B97F4A7C15ULL);
+		sum += h;
+		x ^= h;
+	}
+	for (int o = 16; o; o >>= 1) {
+		desc += __shfl_xor_sync(0xFFFFFFFFu, desc, o);
+		sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+		x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		atomicAdd(&out3[0], desc);
+		atomicAdd(&out3[1], sum);
+		atomicXor(&out3[2], x);
+	}
+}
+
+inline int grid_for(size_t n, int threads, int cap) {
+	size_t g = (n + threads - 1) / threads;
+	if (g < 1) g = 1;
+	return (int)(g > (size_t)cap ? (size_t)cap : g);
+}
+
+} // namespace
+
+cudaError_t launch_iota_if_early(void *ib, int idx_bytes, size_t n, const Ctl *ctl, cudaStream_t st) {
+	const int g = grid_for(n, 256, 148 * 8);
+	switch (idx_bytes) {
+	case 1: iota_if_early_kernel<<<g, 256, 0, st>>>(static_cast<uint8_t *>(ib), n, ctl); break;
+	case 2: iota_if_early_kernel<<<g, 256, 0, st>>>(static_cast<uint16_t *>(ib), n, ctl); break;
+	case 4: iota_if_early_kernel<<<g, 256, 0, st>>>(static_cast<uint32_t *>(ib), n, ctl); break;
+	case 8: iota_if_early_kernel<<<g, 256, 0, st>>>(static_cast<unsigned long long *>(ib), n, ctl); break;
+	default: return cudaErrorInvalidValue;
+	}
+	count_launch();
+	return cudaGetLastError();
+}
+
+cudaError_t launch_narrow_index(const uint32_t *w0, const uint32_t *w1, void *ib, int idx_bytes, size_t n,
+                                const Ctl *ctl, cudaStream_t st) {
+	const int g = grid_for(n, 256, 148 * 8);
+	switch (idx_bytes) {
+	case 1: narrow_index_kernel<<<g, 256, 0, st>>>(w0, w1, static_cast<uint8_t *>(ib), n, ctl); break;
+	case 2: narrow_index_kernel<<<g, 256, 0, st>>>(w0, w1, static_cast<uint16_t *>(ib), n, ctl); break;
+	default: return cudaErrorInvalidValue;
+	}
+	count_launch();
+	return cudaGetLastError();
+}
+
+cudaError_t launch_fill(void *dst, size_t count, int key_bytes, uint64_t seed, uint64_t start, int dist,
+                        uint64_t mask, uint64_t orv, cudaStream_t st) {
+	const int g = grid_for(count, 256, 148 * 16);
+	switch (key_bytes) {
+	case 1: fill_kernel<<<g, 256, 0, st>>>(static_cast<uint8_t *>(dst), count, seed, start, dist, mask, orv); break;
+	case 2: fill_kernel<<<g, 256, 0, st>>>(static_cast<uint16_t *>(dst), count, seed, start, dist, mask, orv); break;
+	case 4: fill_kernel<<<g, 256, 0, st>>>(static_cast<uint32_t *>(dst), count, seed, start, dist, mask, orv); break;
+	case 8: fill_kernel<<<g, 256, 0, st>>>(static_cast<unsigned long long *>(dst), count, seed, start, dist, mask, orv); break;
+	default: return cudaErrorInvalidValue;
+	}
+	count_launch();
+	return cudaGetLastError();
+}
+
+cudaError_t launch_verify(const void *data, size_t n, uint32_t record_bytes, const KeyDesc &kd,
+                          unsigned long long *out3, int num_sms, cudaStream_t st) {
+	const int g = grid_for(n, 256, num_sms * 8);
+	switch (record_bytes) {
+	case 1: verify_kernel<1><<<g, 256, 0, st>>>(static_cast<const uint8_t *>(data), n, kd, out3); break;
+	case 2: verify_kernel<2><<<g, 256, 0, st>>>(static_cast<const uint16_t *>(data), n, kd, out3); break;
+	case 4: verify_kernel<4><<<g, 256, 0, st>>>(static_cast<const uint32_t *>(data), n, kd, out3); break;
+	case 8: verify_kernel<8><<<g, 256, 0, st>>>(static_cast<const unsigned long long *>(data), n, kd, out3); break;
+	case 16: verify_kernel<16><<<g, 256, 0, st>>>(static_cast<const ulonglong2 *>(data), n, kd, out3); break;
+	default: return cudaErrorInvalidValue;
+	}
+	count_launch();
+	return cudaGetLastError();
+}
+
+} // namespace rsx
