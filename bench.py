@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: Gkeys/s sorted on B200, next to the HBM roofline and the
+reference's CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One "step" = one complete sort of the workload (histogram + setup + every live scatter pass)
+through the C ABI (librsx.so).  The input is restored from a pristine device copy OUTSIDE the
+timed region before every step (the reference's own Google-Benchmark loop forgets to do this,
+radix_bench.cpp:91-93); each step is timed with CUDA events on the launch stream.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+_M64 = (1 << 64) - 1
+# name -> (element type, keys per GPU, dist, mask, orv, live passes)
+WORKLOADS = {
+    "1B-u32-uniform": ("u32", 1_000_000_000, "uniform", _M64, 0, 4),       # BASELINE configs[1] (u32 half)
+    "1B-u64-uniform": ("u64", 1_000_000_000, "uniform", _M64, 0, 8),       # BASELINE configs[1] (u64 half)
+    "40M-u32-uniform": ("u32", 40_000_000, "uniform", _M64, 0, 4),         # BASELINE configs[0]
+    "1B-u32-mask24": ("u32", 1_000_000_000, "uniform", 0x00FFFFFF, 0, 3),  # column skipping, README.md:889-891
+    "1B-u64-consthi": ("u64", 1_000_000_000, "uniform", 0x000000FFFFFFFFFF, 0xAA00000000000000, 5),
+    "500M-f32": ("f32", 500_000_000, "uniform", _M64, 0, 4),               # BASELINE configs[2]
+    "500M-i64": ("i64", 500_000_000, "uniform", _M64, 0, 8),
+    "2B-u64-uniform": ("u64", 2_000_000_000, "uniform", _M64, 0, 8),       # per-GPU shard of configs[4]
+}
+CPU_SAMPLE_KEYS = {4: 256_000_000, 8: 96_000_000}  # bounded CPU sample, ~10-30 s of single-core work
+
+
+def _torch_dtype(torch, tname):
+    return {"u32": torch.int32, "u64": torch.int64, "i32": torch.int32, "i64": torch.int64,
+            "f32": torch.float32, "f64": torch.float64}[tname]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()  # the exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference_run(tname, n, dist, mask, orv, repeats=1):
+    """Times the reference's CPU radix_sort (oracle/_ref when present, else the oracle port) on one
+    core -- the reference is single-threaded by construction.  Both buffers are pre-faulted."""
+    import numpy as np
+    import pyoracle
+    keygen = importlib.import_module("radix-sorting_b200.keygen")
+    t = pyoracle.TYPES[tname]
+    keys = np.empty(n, dtype=f"<u{t.key_bytes}")
+    CH = 1 << 24
+    for s in range(0, n, CH):
+        keys[s:s + CH] = keygen.fill(7, s, min(CH, n - s), t.key_bytes, dist, mask, orv)
+    src = keys.view(t.dtype)
+    aux = np.zeros_like(src)
+    try:
+        os.sched_setaffinity(0, {sorted(os.sched_getaffinity(0))[0]})
+    except Exception:
+        pass
+    best = None
+    if os.path.exists(pyoracle.LIB_REF):
+        ref, kind = pyoracle.Ref(), "reference"
+        for _ in range(repeats):
+            work = src.copy()
+            aux[:] = 0
+            t0 = time.perf_counter()
+            ref.radix_sort_inplace(t, work, aux)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    else:
+        import ctypes as C
+        orc, kind = pyoracle.Oracle(), "port"
+        L = t.layout()
+        for _ in range(repeats):
+            work = src.copy()
+            aux[:] = 0
+            t0 = time.perf_counter()
+            orc.L.orc_radix_sort(work.ctypes.data_as(C.c_void_p), aux.ctypes.data_as(C.c_void_p), n,
+                                 C.byref(L), None, None)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return {"value": n / best / 1e9, "unit": "Gkeys/s", "cores": 1, "kind": kind,
+            "sample": f"{n} {tname} keys ({dist}), one radix_sort call, buffers pre-faulted, best of {repeats}",
+            "seconds": best, "host_cpus": os.cpu_count()}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    tname, n_full, dist, mask, orv, passes = WORKLOADS[args.workload]
+    import pyoracle
+    kb = pyoracle.TYPES[tname].key_bytes
+    n = min(n_full, CPU_SAMPLE_KEYS[kb] // 4)  # each step is a bounded sample; K+W of them must end in minutes
+    times = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        last = cpu_reference_run(tname, n, dist, mask, orv, repeats=1)
+        if i >= args.warmup:
+            times.append(last["seconds"])
+    ms = 1e3 * sum(times) / len(times)
+    val = n / (ms / 1e3) / 1e9
+    last["value"] = val
+    last["sample"] = f"{n} of {n_full} {tname} keys per step, one radix_sort call per step"
+    print(json.dumps({
+        "impl": "reference", "metric": "Gkeys/s sorted", "value": val, "unit": "Gkeys/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": tname, "data": "synthetic",
+        "config": {"workload": args.workload, "keys_per_step": n, "note": "reference CPU path, 1 core (single-threaded by construction)"},
+        "cpu_baseline": last,
+        "e2e": {"value": val, "unit": "Gkeys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload is None:
+        args.workload = "1B-u32-uniform" if max(world, args.gpus) == 1 else "2B-u64-uniform"
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rsx = importlib.import_module("radix-sorting_b200")  # raises if librsx.so is missing: no fallback
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU path"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    tname, n, dname, mask, orv, passes = WORKLOADS[args.workload]
+    tdt = _torch_dtype(torch, tname)
+    kf = rsx.default_kdf(tdt) if tname[0] != "u" else rsx.KeyFunc(rsx.KDF_UNSIGNED)
+    kb = torch.empty(0, dtype=tdt).element_size()
+
+    if world > 1:
+        dsort = importlib.import_module("radix-sorting_b200.dist")
+        result = dsort.bench_partitioned(args, rsx, tname, n, dname, mask, orv, rank, world, dev)
+        if rank == 0:
+            print(json.dumps(result))
+        dist.destroy_process_group()
+        return
+
+    pristine = torch.empty(n, dtype=tdt, device=dev)
+    rsx.fill_keys(pristine, seed=2 + rank, dist=dname, mask=mask, orv=orv)
+    src = torch.empty_like(pristine)
+    aux = torch.empty_like(pristine)
+    rsx.reserve(rsx.workspace_bytes(n, kf.layout(kb)))
+    rsx.set_profile(True)
+    d0, s0, x0 = rsx.verify(pristine, kf)
+
+    def step():
+        src.copy_(pristine)  # restore: outside the events; also evicts L2 (4-8 GB >> 126 MB)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rep = rsx.RsxReport()
+        e0.record()
+        res = rsx.radix_sort(src, aux, None, kf, report=rep)
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1), rep, res, rsx.get_profile()
+
+    for _ in range(args.warmup):
+        _, rep, res, _ = step()
+    d1, s1, x1 = rsx.verify(res, kf)
+    assert d1 == 0 and (s1, x1) == (s0, x0), "warm-up result is not a sorted permutation of the input"
+    assert rep.ncols == passes, (rep.ncols, passes)
+
+    sampler = ClockSampler(local_rank)
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = rsx.total_kernel_launches()
+    times, profs = [], []
+    torch.cuda.synchronize()
+    for _ in range(args.steps):
+        ms, rep, res, prof = step()
+        times.append(ms)
+        profs.append(prof)
+    torch.cuda.synchronize()
+    launches = rsx.total_kernel_launches() - launches0
+    clocks = sampler.stop()
+
+    ms_per_step = sum(times) / len(times)
+    value = n / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel: the scatter pass (K3) --------------------------------
+    peak, peak_src = measured_peak()
+    pass_ms = [p[2 + c] for p in profs for c in range(kb) if len(p) > 2 + c and p[2 + c] > 0 and (rep.live_mask >> c) & 1]
+    hist_ms = [p[0] for p in profs if p]
+    avg_pass = sum(pass_ms) / len(pass_ms)
+    alg_bytes_pass = 2 * n * kb  # read n records + write n records (2K per key per pass)
+    achieved = alg_bytes_pass / (avg_pass * 1e-3) / 1e9
+    alg_bytes_sort = n * kb * (1 + 2 * passes)
+    roofline = {
+        "bound": "hbm", "kernel": "scatter_kernel (K3, one launch per live column)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_pass, "ms_per_launch": avg_pass,
+        "launches_timed": len(pass_ms),
+        "histogram_kernel": {"ms": sum(hist_ms) / len(hist_ms), "alg_bytes": n * kb,
+                             "achieved": n * kb / (sum(hist_ms) / len(hist_ms) * 1e-3) / 1e9,
+                             "frac": n * kb / (sum(hist_ms) / len(hist_ms) * 1e-3) / 1e9 / peak},
+        "whole_sort": {"alg_bytes": alg_bytes_sort, "achieved": alg_bytes_sort / (ms_per_step * 1e-3) / 1e9,
+                       "frac": alg_bytes_sort / (ms_per_step * 1e-3) / 1e9 / peak,
+                       "frac_of_nominal_8TBs": alg_bytes_sort / (ms_per_step * 1e-3) / 1e9 / 8000.0},
+    }
+
+    # ---- e2e: the same sort through the C ABI with HOST buffers (H2D + sort + D2H timed) ----------
+    e2e = None
+    if not args.no_e2e:
+        del src, aux
+        torch.cuda.empty_cache()
+        h_src = torch.empty(n, dtype=tdt, pin_memory=True)
+        h_aux = torch.empty(n, dtype=tdt, pin_memory=True)
+        h_pristine = pristine.cpu()
+        e2e_times = []
+        for i in range(1 + min(3, args.steps)):
+            h_src.copy_(h_pristine)
+            t0 = time.perf_counter()
+            res_h = rsx.radix_sort(h_src, h_aux, None, kf)
+            dt = time.perf_counter() - t0
+            if i:
+                e2e_times.append(dt)
+        chk = res_h[:: max(1, n // 1_000_000)].to(torch.float64 if tname[0] == "f" else torch.int64)
+        e2e_s = sum(e2e_times) / len(e2e_times)
+        e2e = {"value": n / e2e_s / 1e9, "unit": "Gkeys/s", "h2d_bytes_per_step": n * kb, "d2h_bytes_per_step": n * kb,
+               "ms_per_step": e2e_s * 1e3, "steps": len(e2e_times),
+               "note": "rsx_sort on pinned HOST buffers: H2D + sort + D2H inside the timed call (wall clock)"}
+        del h_src, h_aux, h_pristine, chk
+
+    cpu = None
+    if not args.no_cpu:
+        cpu = cpu_reference_run(tname, min(n, CPU_SAMPLE_KEYS[kb]), dname, mask, orv, repeats=1)
+
+    out = {
+        "metric": "Gkeys/s sorted", "value": value, "unit": "Gkeys/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": tname, "data": "synthetic",
+        "config": {"workload": args.workload, "keys": n, "key_bytes": kb, "live_passes": passes,
+                   "dist": dname, "l2": "inputs (n*key_bytes) larger than L2 and restored by a full-size copy before every step",
+                   "timing": "CUDA events around each rsx_sort call on the launch stream, mean of steps",
+                   "ms_min": min(times), "ms_max": max(times)},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

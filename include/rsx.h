@@ -133,8 +133,15 @@ const char *rsx_strerror(int status);
 const char *rsx_last_cuda_error(void); /* thread-local text of the last failing CUDA call */
 int rsx_version(void);
 uint64_t rsx_total_kernel_launches(void); /* process-wide count, for bench.py's gpu_launches */
-/* Tuning/debug knob: 0 = default.  See DESIGN.md "variants". */
+/* Options: "profile" (0/1): bracket every kernel of rsx_sort / rsx_sort_rank with CUDA events on
+ * the launch stream so that per-kernel device times can be read back with rsx_get_profile
+ * (bench.py's roofline leg; off by default because the extra events perturb nothing but are
+ * not free). */
 int rsx_set_option(const char *name, long value);
+/* Device time in ms of each kernel of the LAST profiled sort on this thread, in launch order:
+ * [0] histogram (K1), [1] setup (K2), [2 + c] scatter pass of column c (0 if trivial/skipped).
+ * Returns the number of entries written (<= cap), or a negative rsx_status. */
+int rsx_get_profile(float *ms_out, int cap);
 
 #ifdef __cplusplus
 }

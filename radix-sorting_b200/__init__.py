@@ -38,6 +38,7 @@ EXPORTS = [
     "rsx_sort", "rsx_sort_rank", "rsx_histogram", "rsx_scatter_pass", "rsx_workspace_bytes",
     "rsx_reserve", "rsx_release", "rsx_fill_keys", "rsx_verify", "rsx_strerror",
     "rsx_last_cuda_error", "rsx_version", "rsx_total_kernel_launches", "rsx_set_option",
+    "rsx_get_profile",
 ]
 
 
@@ -106,6 +107,8 @@ def _lib() -> C.CDLL:
     L.rsx_total_kernel_launches.argtypes = []
     L.rsx_set_option.restype = C.c_int
     L.rsx_set_option.argtypes = [C.c_char_p, C.c_long]
+    L.rsx_get_profile.restype = C.c_int
+    L.rsx_get_profile.argtypes = [C.POINTER(C.c_float), C.c_int]
     _LIB = L
     return L
 
@@ -303,6 +306,17 @@ def reserve(nbytes: int) -> None:
 
 def workspace_bytes(n: int, layout: RsxLayout, rank_idx_bytes: int = 0) -> int:
     return int(_lib().rsx_workspace_bytes(n, C.byref(layout), rank_idx_bytes))
+
+
+def set_profile(on: bool) -> None:
+    _lib().rsx_set_option(b"profile", 1 if on else 0)
+
+
+def get_profile():
+    """Per-kernel device ms of the last profiled sort: [K1, K2, pass col0, pass col1, ...]."""
+    buf = (C.c_float * 16)()
+    k = _lib().rsx_get_profile(buf, 16)
+    return [float(buf[i]) for i in range(max(k, 0))]
 
 
 def total_kernel_launches() -> int:

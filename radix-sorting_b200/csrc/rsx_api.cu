@@ -25,6 +25,45 @@ namespace {
 
 thread_local char t_err[512] = "";
 
+// ---- optional per-kernel profiling (rsx_set_option("profile", 1)) ------------------------------
+std::atomic<int> g_profile{0};
+constexpr int kMaxProf = 2 + kMaxCols;
+struct Prof {
+	cudaEvent_t ev[kMaxProf + 1] = {};
+	bool created = false;
+	int count = 0; // events recorded - 1 = intervals
+	float ms[kMaxProf] = {};
+	int n_ms = 0;
+};
+thread_local Prof t_prof;
+
+void prof_mark(cudaStream_t st, bool first = false) {
+	if (!g_profile.load(std::memory_order_relaxed))
+		return;
+	Prof &P = t_prof;
+	if (!P.created) {
+		for (auto &e : P.ev)
+			cudaEventCreate(&e);
+		P.created = true;
+	}
+	if (first)
+		P.count = 0;
+	if (P.count <= kMaxProf)
+		cudaEventRecord(P.ev[P.count++], st);
+}
+void prof_collect() {
+	if (!g_profile.load(std::memory_order_relaxed))
+		return;
+	Prof &P = t_prof;
+	P.n_ms = 0;
+	for (int i = 0; i + 1 < P.count; ++i) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, P.ev[i], P.ev[i + 1]) != cudaSuccess)
+			ms = -1.f;
+		P.ms[P.n_ms++] = ms;
+	}
+}
+
 int fail_cuda(cudaError_t e, const char *what) {
 	snprintf(t_err, sizeof(t_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
 	(void)cudaGetLastError(); // clear the sticky-free error state
@@ -214,19 +253,23 @@ int run_scatter(const PassBuffers &pb, const Plan &P, int col, WsHead *ws, bool 
 int enqueue_front(const void *src, const Plan &P, unsigned char *wsp, int num_sms, cudaStream_t st) {
 	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
 	CU(cudaMemsetAsync(wsp, 0, kWsZeroBytes, st));
+	CU(cudaMemsetAsync(wsp + P.off_status, 0, P.status_bytes_per_col * P.kd.key_bytes, st));
+	prof_mark(st, true);
 	CU(launch_histogram(src, P.n, P.rb, P.kd, ws, num_sms, st));
+	prof_mark(st);
 	CU(launch_setup(src, P.n, P.rb, P.kd, ws, st));
+	prof_mark(st);
 	return RSX_OK;
 }
 
 int enqueue_passes(const PassBuffers &pb, const Plan &P, unsigned char *wsp, int num_sms, cudaStream_t st) {
 	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
-	CU(cudaMemsetAsync(wsp + P.off_status, 0, P.status_bytes_per_col * P.kd.key_bytes, st));
 	for (uint32_t c = 0; c < P.kd.key_bytes; ++c) {
 		int r = run_scatter(pb, P, (int)c, ws, false, wsp + P.off_status + c * P.status_bytes_per_col,
 		                    &ws->tickets[c], num_sms, st);
 		if (r)
 			return r;
+		prof_mark(st);
 	}
 	return RSX_OK;
 }
@@ -236,6 +279,7 @@ int read_ctl(const unsigned char *wsp, Ctl *pinned, cudaStream_t st, unsigned lo
 	const WsHead *ws = reinterpret_cast<const WsHead *>(wsp);
 	CU(cudaMemcpyAsync(pinned, &ws->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	prof_collect();
 	if (rep) {
 		rep->early_exit = pinned->early_exit;
 		rep->ncols = pinned->early_exit ? 0 : pinned->ncols;
@@ -328,9 +372,20 @@ const char *rsx_last_cuda_error(void) { return t_err; }
 uint64_t rsx_total_kernel_launches(void) { return g_launches.load(); }
 
 int rsx_set_option(const char *name, long value) {
-	(void)name;
-	(void)value;
-	return RSX_ERR_INVALID; // no tunables in this build
+	if (name && strcmp(name, "profile") == 0) {
+		g_profile.store(value ? 1 : 0);
+		return RSX_OK;
+	}
+	return RSX_ERR_INVALID;
+}
+
+int rsx_get_profile(float *ms_out, int cap) {
+	if (!ms_out || cap < 0)
+		return RSX_ERR_INVALID;
+	const int k = t_prof.n_ms < cap ? t_prof.n_ms : cap;
+	for (int i = 0; i < k; ++i)
+		ms_out[i] = t_prof.ms[i];
+	return k;
 }
 
 size_t rsx_workspace_bytes(size_t n, const rsx_layout *layout, int rank_idx_bytes) {
@@ -629,7 +684,6 @@ int rsx_scatter_pass(const void *src, void *dst, const void *payload_src, void *
 	const int sms = g_dev[dev].num_sms;
 	if ((r = enqueue_front(src, P, wsp, sms, st))) // histogram + scan give this column's offsets
 		return r;
-	CU(cudaMemsetAsync(wsp + P.off_status, 0, P.status_bytes_per_col, st));
 	PassBuffers pb{};
 	pb.rec_first = src;
 	pb.rec_buf[0] = dst;

@@ -1,0 +1,320 @@
+"""GPU parity tests: the CUDA path (through the C ABI in librsx.so) against the oracle and the
+committed golden digests of the unmodified reference.  Bit-exact: this is integer/byte work.
+
+Run on the B200 box: python -m pytest tests -m gpu
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cases import GOLDEN_CASES, case_id, digest, make_input
+from pyoracle import TYPES
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REF_OUT = json.load(open(os.path.join(GOLD, "ref_outputs.json")))
+VEC = json.load(open(os.path.join(GOLD, "reference_vectors.json")))
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the product has no CPU path (run with -m gpu on the GPU box)")
+    return torch
+
+
+def to_dev(torch, a: np.ndarray):
+    """numpy (any dtype, incl. structured) -> uint8 CUDA tensor with the same bytes."""
+    raw = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+    return torch.from_numpy(raw.copy()).cuda()
+
+
+def kf_for(rsx, tname, descending=False):
+    t = TYPES[tname]
+    return rsx.KeyFunc(t.kdf_kind, descending, t.record_bytes, t.key_offset, t.key_bytes)
+
+
+def gpu_sort(rsx, torch, tname, data, descending=False):
+    src = to_dev(torch, data)
+    aux = torch.full_like(src, 0xCD)
+    rep = rsx.RsxReport()
+    res = rsx.radix_sort(src, aux, None, kf_for(rsx, tname, descending), report=rep)
+    torch.cuda.synchronize()
+    return res.cpu().numpy(), rep, (res.data_ptr() == aux.data_ptr() and data.shape[0] > 0)
+
+
+def gpu_rank(rsx, torch, tname, data, idx_dtype=np.uint32, descending=False):
+    src = to_dev(torch, data)
+    before = src.clone()
+    n = data.shape[0]
+    ib_np = np.full(2 * n, 0xEE, dtype=idx_dtype)
+    ib = torch.from_numpy(ib_np.view(np.uint8).copy()).cuda().view(
+        {1: torch.uint8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[np.dtype(idx_dtype).itemsize])
+    rep = rsx.RsxReport()
+    res = rsx.radix_sort_rank(src, ib, n, kf_for(rsx, tname, descending), report=rep)
+    torch.cuda.synchronize()
+    assert torch.equal(src, before), "rank sort must not modify src (const T*, radix_sort_rank.hpp:97)"
+    ranks = res.cpu().numpy().view(idx_dtype)
+    return ranks, rep, ib.cpu().numpy().view(idx_dtype)
+
+
+# ---- golden digests of the unmodified reference --------------------------------------------------
+
+@pytest.mark.parametrize("c", GOLDEN_CASES, ids=case_id)
+def test_sort_matches_reference_golden(rsx, torch, oracle, c):
+    t = TYPES[c[0]]
+    data = make_input(c[0], c[1], 1234, c[2], c[3], c[4])
+    out, rep, in_aux = gpu_sort(rsx, torch, c[0], data)
+    g = REF_OUT["sort"][case_id(c)]
+    want, orep, hist = oracle.radix_sort(data, t.layout(), want_hist=True)
+    assert out.tobytes() == want.tobytes()
+    assert digest(out) == g["sha256"]
+    assert int(in_aux) == g["result_in_aux"] == rep.result_in_aux
+    assert rep.early_exit == orep.early_exit and rep.ncols == orep.ncols
+    assert rep.live_mask == sum(1 << orep.cols[i] for i in range(orep.ncols))
+    if case_id(c) in REF_OUT["sort_desc"]:
+        out, rep, in_aux = gpu_sort(rsx, torch, c[0], data, descending=True)
+        g = REF_OUT["sort_desc"][case_id(c)]
+        assert digest(out) == g["sha256"] and int(in_aux) == g["result_in_aux"]
+
+
+@pytest.mark.parametrize("c", [c for c in GOLDEN_CASES if c[1] in (2, 257, 1000, 5000, 70001)], ids=case_id)
+def test_rank_matches_oracle(rsx, torch, oracle, c):
+    t = TYPES[c[0]]
+    data = make_input(c[0], c[1], 1234, c[2], c[3], c[4])
+    for idt in (np.uint32, np.uint64):
+        ranks, rep, ib = gpu_rank(rsx, torch, c[0], data, idt)
+        want, orep, oib = oracle.radix_sort_rank(data, t.layout(), idt)
+        assert np.array_equal(ranks, want)
+        assert rep.result_in_aux == orep.result_in_aux and rep.ncols == orep.ncols
+        if orep.early_exit:  # identity in the FIRST half (radix_sort_rank.hpp:52-57)
+            assert np.array_equal(ib[:c[1]], np.arange(c[1], dtype=idt))
+    # where the shipped header is right (<= 1 live column / early exit) we match it bit for bit
+    cid = case_id(c)
+    if cid in REF_OUT["rank_as_shipped"] and orep.ncols <= 1:
+        ranks, rep, _ = gpu_rank(rsx, torch, c[0], data, np.uint32)
+        assert digest(ranks) == REF_OUT["rank_as_shipped"][cid]["sha256"]
+
+
+# ---- the reference's own test vectors ----------------------------------------------------------------
+
+def _records(layout, keys):
+    rb, ko, kb = layout[0], layout[1], layout[2]
+    raw = np.zeros((len(keys), rb), dtype=np.uint8)
+    for i, k in enumerate(keys):
+        raw[i, ko:ko + kb] = np.frombuffer(int(k).to_bytes(kb, "little"), dtype=np.uint8)
+        if rb >= kb + 4:
+            raw[i, rb - 4:rb] = np.frombuffer(int(i).to_bytes(4, "little"), dtype=np.uint8)
+    return raw
+
+
+@pytest.mark.parametrize("v", VEC["value_sorts"], ids=lambda v: v["name"][:40])
+def test_reference_value_vectors(rsx, torch, v):
+    rb, ko, kb, kind, flags = v["layout"]
+    raw = _records(v["layout"], v["keys"])
+    src = torch.from_numpy(raw.reshape(-1).copy()).cuda()
+    aux = torch.zeros_like(src)
+    rep = rsx.RsxReport()
+    res = rsx.radix_sort(src, aux, None, rsx.KeyFunc(kind, bool(flags & 1), rb, ko, kb), report=rep)
+    out = res.cpu().numpy().reshape(-1, rb)
+    order = [int.from_bytes(out[i, -4:].tobytes(), "little") for i in range(len(v["keys"]))]
+    assert order == v["order"]
+    assert rep.result_in_aux == v["result_in_aux"]
+    assert (res.data_ptr() == aux.data_ptr()) == bool(v["result_in_aux"])
+
+
+def test_reference_float_vector(rsx, torch):
+    v = VEC["float_sort"]
+    data = np.array([int(x, 16) for x in v["input_bits"]], dtype=np.uint32).view(np.float32)
+    src = torch.from_numpy(data.copy()).cuda()
+    aux = torch.zeros_like(src)
+    res = rsx.radix_sort(src, aux)  # default KDF picked from the dtype, like radix_tests.cpp:163
+    assert [f"{x:08x}" for x in res.cpu().numpy().view(np.uint32)] == v["output_bits"]
+    assert res.data_ptr() == src.data_ptr()
+
+
+@pytest.mark.parametrize("v", VEC["rank_sorts"], ids=lambda v: v["name"][:40])
+def test_reference_rank_vectors(rsx, torch, v):
+    rb, ko, kb, kind, flags = v["layout"]
+    raw = _records(v["layout"], v["keys"])
+    n = len(v["keys"])
+    src = torch.from_numpy(raw.reshape(-1).copy()).cuda()
+    tdt = {1: torch.uint8, 4: torch.int32}[v["idx_bytes"]]
+    ib = torch.zeros(2 * n, dtype=tdt, device="cuda")
+    rep = rsx.RsxReport()
+    res = rsx.radix_sort_rank(src, ib, n, rsx.KeyFunc(kind, bool(flags & 1), rb, ko, kb), report=rep)
+    assert res.cpu().numpy().astype(np.int64).tolist() == v["ranks"]
+    assert rep.result_in_aux == v["result_in_aux"]
+
+
+def test_int_then_reverse_resort(rsx, torch, oracle):
+    """radix_tests.cpp:179-207: sort 50 000 ints, then re-sort the RESULT descending with
+    kdf_int_reverse, passing the other buffer as aux."""
+    rng = np.random.default_rng(0)
+    vals = np.clip(rng.normal(-2147483648.0, 2147483647.0, 50000), -2147483648.0, 2147483647.0).astype(np.int32)
+    src = torch.from_numpy(vals.copy()).cuda()
+    aux = torch.zeros_like(src)
+    res = rsx.radix_sort(src, aux)
+    assert np.array_equal(res.cpu().numpy(), np.sort(vals, kind="stable"))
+    other = aux if res.data_ptr() == src.data_ptr() else src
+    res2 = rsx.radix_sort(res, other, None, rsx.default_kdf(torch.int32, descending=True))
+    assert np.array_equal(res2.cpu().numpy(), np.sort(vals, kind="stable")[::-1])
+
+
+# ---- halves of the path --------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("tname", ["u8", "u16", "u32", "u64", "i32", "i64", "f32", "f64", "rec8_u32", "rec16_u8", "rec16_u64"])
+@pytest.mark.parametrize("n,dist,mask", [(2, "uniform", -1), (1000, "uniform", -1), (300001, "uniform", -1),
+                                          (300001, "uniform", 0x00FF00FF00FF00FF), (50000, "sorted", -1),
+                                          (50000, "constant", -1), (262144, "and3", -1)])
+def test_histogram_kernel(rsx, torch, oracle, tname, n, dist, mask):
+    t = TYPES[tname]
+    data = make_input(tname, n, 99, dist, mask & ((1 << 64) - 1))
+    hist, descents, rep = rsx.histogram(to_dev(torch, data), kf_for(rsx, tname))
+    _, orep, ohist = oracle.radix_sort(data, t.layout(), want_hist=True)
+    assert np.array_equal(hist, ohist)
+    assert descents + 1 == orep.n_unsorted  # n_unsorted = n - #ordered pairs = 1 + descents
+    assert rep.early_exit == orep.early_exit
+    if not orep.early_exit:
+        assert rep.live_mask == sum(1 << orep.cols[i] for i in range(orep.ncols))
+
+
+@pytest.mark.parametrize("off", [1, 2, 3, 5])
+def test_unaligned_pointers(rsx, torch, oracle, off):
+    """Buffers that are element-aligned but not 16-byte aligned (head/tail path of K1)."""
+    n = 100003
+    data = make_input("u32", n, 7)
+    base = torch.zeros(n + 8, dtype=torch.int32, device="cuda")
+    base2 = torch.zeros(n + 8, dtype=torch.int32, device="cuda")
+    src = base[off:off + n]
+    src.copy_(torch.from_numpy(data.view(np.int32).copy()).cuda())
+    aux = base2[off:off + n]
+    res = rsx.radix_sort(src, aux, None, rsx.KeyFunc(rsx.KDF_UNSIGNED))
+    want, _, _ = oracle.radix_sort(data, TYPES["u32"].layout())
+    assert np.array_equal(res.cpu().numpy().view(np.uint32), want)
+
+
+@pytest.mark.parametrize("tname,col", [("u32", 0), ("u32", 3), ("u64", 5), ("i32", 3), ("f32", 3), ("f32", 1), ("f64", 7), ("rec8_u32", 2)])
+def test_single_scatter_pass_is_stable(rsx, torch, oracle, tname, col):
+    """One K3 pass == one stable counting-sort pass on that column (radix_sort.hpp:83-88)."""
+    t = TYPES[tname]
+    n = 200001
+    data = make_input(tname, n, 11, "and2")
+    src = to_dev(torch, data)
+    dst = torch.zeros_like(src)
+    pl_src = torch.arange(n, dtype=torch.int32, device="cuda")
+    pl_dst = torch.zeros_like(pl_src)
+    rsx.scatter_pass(src, dst, col, kf_for(rsx, tname), pl_src, pl_dst)
+    torch.cuda.synchronize()
+    # vectorised derived digits
+    keys = data["key"] if data.dtype.names else data
+    u = keys.view(f"<u{t.key_bytes}").astype(np.uint64)
+    top = np.uint64(1 << (8 * t.key_bytes - 1))
+    m = np.uint64((1 << (8 * t.key_bytes)) - 1)
+    if t.kdf_kind == 1:
+        u = u ^ top
+    elif t.kdf_kind == 2:
+        u = np.where(u & top, u ^ m, u ^ top)
+    digits = ((u >> np.uint64(8 * col)) & np.uint64(0xFF)).astype(np.int64)
+    perm = np.argsort(digits, kind="stable")
+    assert np.array_equal(pl_dst.cpu().numpy(), perm.astype(np.int32))
+    assert dst.cpu().numpy().tobytes() == data[perm].tobytes()
+
+
+# ---- edges --------------------------------------------------------------------------------------------------
+
+def test_trivial_sizes(rsx, torch):
+    for n in (0, 1):
+        src = torch.arange(n, dtype=torch.int32, device="cuda")
+        aux = torch.zeros_like(src)
+        rep = rsx.RsxReport()
+        res = rsx.radix_sort(src, aux, report=rep)
+        assert res.data_ptr() == src.data_ptr() and rep.early_exit == 1
+        ib = torch.full((2 * n + 2,), 7, dtype=torch.int32, device="cuda")
+        r = rsx.radix_sort_rank(src, ib, n)
+        assert r.cpu().tolist() == list(range(n))  # radix_sort_rank.hpp:28-32
+
+
+def test_presorted_leaves_buffers_untouched(rsx, torch):
+    n = 1 << 20
+    src = torch.arange(n, dtype=torch.int32, device="cuda")
+    aux = torch.full_like(src, -1)
+    rep = rsx.RsxReport()
+    res = rsx.radix_sort(src, aux, report=rep)
+    assert rep.early_exit == 1 and res.data_ptr() == src.data_ptr()
+    assert torch.equal(src, torch.arange(n, dtype=torch.int32, device="cuda"))
+    assert bool((aux == -1).all())  # radix_sort.hpp:60-62: nothing written
+
+
+def test_host_buffers_are_staged(rsx, torch, oracle):
+    """The reference sorts host memory; host pointers go H2D -> sort -> D2H into the buffer
+    the reference would have returned."""
+    for mask, tname in [((1 << 64) - 1, "u32"), (0x00FFFFFF, "u32"), ((1 << 64) - 1, "u64")]:
+        data = make_input(tname, 300000, 5, "uniform", mask)
+        src = torch.from_numpy(data.view(np.int32 if tname == "u32" else np.int64).copy())
+        aux = torch.zeros_like(src)
+        rep = rsx.RsxReport()
+        res = rsx.radix_sort(src, aux, None, rsx.KeyFunc(rsx.KDF_UNSIGNED), report=rep)
+        want, orep, _ = oracle.radix_sort(data, TYPES[tname].layout())
+        assert rep.staged == 1 and rep.result_in_aux == orep.result_in_aux
+        assert res.numpy().tobytes() == want.tobytes()
+        ib = torch.zeros(2 * 300000, dtype=torch.int32)
+        r = rsx.radix_sort_rank(torch.from_numpy(data.view(np.int32 if tname == "u32" else np.int64).copy()), ib,
+                                300000, rsx.KeyFunc(rsx.KDF_UNSIGNED))
+        wr, _, _ = oracle.radix_sort_rank(data, TYPES[tname].layout(), np.uint32)
+        assert np.array_equal(r.numpy().view(np.uint32), wr)
+
+
+def test_error_paths(rsx, torch):
+    src = torch.zeros(16, dtype=torch.int32, device="cuda")
+    with pytest.raises(rsx.RsxError) as e:  # float KDF needs a 4/8-byte key
+        rsx.radix_sort(src.view(torch.uint8), torch.zeros(64, dtype=torch.uint8, device="cuda"), None,
+                       rsx.KeyFunc(rsx.KDF_FLOAT, False, 2, 0, 2))
+    assert e.value.status == rsx.RSX_ERR_INVALID
+    import ctypes as C
+    res = C.c_void_p()
+    L = rsx.RsxLayout(4, 0, 4, 0, 0)
+    host = torch.zeros(16, dtype=torch.int32)  # host src, device aux
+    st = rsx.lib().rsx_sort(host.data_ptr(), src.data_ptr(), 16, C.byref(L), C.byref(res), None, None)
+    assert st == rsx.RSX_ERR_MIXED_MEMORY
+    with pytest.raises(rsx.RsxError) as e:  # 300 records cannot be ranked with uint8 indices
+        rsx.radix_sort_rank(torch.zeros(300, dtype=torch.int32, device="cuda"),
+                            torch.zeros(600, dtype=torch.uint8, device="cuda"))
+    assert e.value.status == rsx.RSX_ERR_IDX_RANGE
+
+
+# ---- large sizes: size-independent properties (no CPU oracle needed) ---------------------------------------
+
+@pytest.mark.parametrize("tname,n", [("u32", 1 << 26), ("u64", 1 << 25), ("f32", 40_000_000)])
+def test_large_sort_properties(rsx, torch, tname, n):
+    """sortedness (0 descents of the derived key) + multiset checksum before == after, and
+    idempotence: sorting the result again is an early exit."""
+    tdt = {"u32": torch.int32, "u64": torch.int64, "f32": torch.float32}[tname]
+    src = torch.empty(n, dtype=tdt, device="cuda")
+    aux = torch.empty_like(src)
+    rsx.fill_keys(src, seed=42)
+    kf = kf_for(rsx, tname)
+    d0, s0, x0 = rsx.verify(src, kf)
+    assert d0 > 0
+    rep = rsx.RsxReport()
+    res = rsx.radix_sort(src, aux, None, kf, report=rep)
+    d1, s1, x1 = rsx.verify(res, kf)
+    assert d1 == 0 and (s1, x1) == (s0, x0)
+    assert rep.ncols == TYPES[tname].key_bytes
+    other = aux if res.data_ptr() == src.data_ptr() else src
+    rep2 = rsx.RsxReport()
+    res2 = rsx.radix_sort(res, other, None, kf, report=rep2)
+    assert rep2.early_exit == 1 and res2.data_ptr() == res.data_ptr()
+
+
+def test_device_keygen_matches_host(rsx, torch, keygen):
+    for dist in keygen.DISTS:
+        for kb, tdt in [(4, torch.int32), (8, torch.int64)]:
+            dst = torch.empty(10007, dtype=tdt, device="cuda")
+            rsx.fill_keys(dst, seed=17, start=123456789, dist=dist, mask=0x00FFFFFFFFFFFF0F, orv=0x3)
+            want = keygen.fill(17, 123456789, 10007, kb, dist, 0x00FFFFFFFFFFFF0F, 0x3)
+            assert np.array_equal(dst.cpu().numpy().view(f"<u{kb}"), want), (dist, kb)
