@@ -33,6 +33,8 @@ WORKLOADS = {
     "1B-u32-uniform": ("u32", 1_000_000_000, "uniform", _M64, 0, 4),       # BASELINE configs[1] (u32 half)
     "1B-u64-uniform": ("u64", 1_000_000_000, "uniform", _M64, 0, 8),       # BASELINE configs[1] (u64 half)
     "40M-u32-uniform": ("u32", 40_000_000, "uniform", _M64, 0, 4),         # BASELINE configs[0]
+    "256M-u32-uniform": ("u32", 256_000_000, "uniform", _M64, 0, 4),       # profiling size (ncu replays)
+    "256M-u64-uniform": ("u64", 256_000_000, "uniform", _M64, 0, 8),
     "1B-u32-mask24": ("u32", 1_000_000_000, "uniform", 0x00FFFFFF, 0, 3),  # column skipping, README.md:889-891
     "1B-u64-consthi": ("u64", 1_000_000_000, "uniform", 0x000000FFFFFFFFFF, 0xAA00000000000000, 5),
     "500M-f32": ("f32", 500_000_000, "uniform", _M64, 0, 4),               # BASELINE configs[2]
@@ -187,6 +189,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--rank-mode", type=int, default=-1, help="-1 auto (hardware probe), 0 ticket, 1 ballot")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -229,6 +232,8 @@ def main():
     aux = torch.empty_like(pristine)
     rsx.reserve(rsx.workspace_bytes(n, kf.layout(kb)))
     rsx.set_profile(True)
+    rsx.lib().rsx_set_option(b"rank_mode", args.rank_mode)
+    rank_mode = {0: "ticket", 1: "ballot"}[rsx.lib().rsx_set_option(b"query_rank_mode", 0)]
     d0, s0, x0 = rsx.verify(pristine, kf)
 
     def step():
@@ -317,7 +322,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": tname, "data": "synthetic",
         "config": {"workload": args.workload, "keys": n, "key_bytes": kb, "live_passes": passes,
-                   "dist": dname, "l2": "inputs (n*key_bytes) larger than L2 and restored by a full-size copy before every step",
+                   "dist": dname, "rank_mode": rank_mode, "l2": "inputs (n*key_bytes) larger than L2 and restored by a full-size copy before every step",
                    "timing": "CUDA events around each rsx_sort call on the launch stream, mean of steps",
                    "ms_min": min(times), "ms_max": max(times)},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),

@@ -133,7 +133,9 @@ const char *rsx_strerror(int status);
 const char *rsx_last_cuda_error(void); /* thread-local text of the last failing CUDA call */
 int rsx_version(void);
 uint64_t rsx_total_kernel_launches(void); /* process-wide count, for bench.py's gpu_launches */
-/* Options: "profile" (0/1): bracket every kernel of rsx_sort / rsx_sort_rank with CUDA events on
+/* Options: "rank_mode" (-1 auto [default]: per-device hardware probe picks the one-instruction
+ * ticket ranking or the ballot ranking, 0 force ticket, 1 force ballot; DESIGN.md "K3");
+ * "query_rank_mode" returns the mode in effect (0 / 1).  "profile" (0/1): bracket every kernel of rsx_sort / rsx_sort_rank with CUDA events on
  * the launch stream so that per-kernel device times can be read back with rsx_get_profile
  * (bench.py's roofline leg; off by default because the extra events perturb nothing but are
  * not free). */

@@ -80,6 +80,7 @@ int fail_cuda(cudaError_t e, const char *what) {
 struct DeviceState {
 	std::mutex mu;
 	int num_sms = 0;
+	int rank_mode = -1; // -1 = not probed yet
 	void *ws = nullptr;
 	size_t ws_bytes = 0;
 	bool busy = false;
@@ -97,6 +98,28 @@ int current_device(int *dev) {
 	if (D.num_sms == 0)
 		CU(cudaDeviceGetAttribute(&D.num_sms, cudaDevAttrMultiProcessorCount, *dev));
 	return RSX_OK;
+}
+
+std::atomic<int> g_rank_override{-1};
+
+// Decide once per device whether the one-instruction ticket ranking is usable (see
+// rsx_scatter.cuh).  Any failure to run the probe selects the provably stable ballot ranking.
+int probe_rank_mode(int dev) {
+	DeviceState &D = g_dev[dev];
+	std::lock_guard<std::mutex> lk(D.mu);
+	if (D.rank_mode >= 0)
+		return D.rank_mode;
+	int mode = RANK_BALLOT;
+	unsigned long long *d = nullptr, h = ~0ULL;
+	if (cudaMalloc((void **)&d, sizeof(*d)) == cudaSuccess) {
+		if (cudaMemset(d, 0, sizeof(*d)) == cudaSuccess && launch_ticket_probe(d, D.num_sms ? D.num_sms : 148, 0) == cudaSuccess &&
+		    cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h == 0)
+			mode = RANK_TICKET;
+		cudaFree(d);
+	}
+	(void)cudaGetLastError();
+	D.rank_mode = mode;
+	return mode;
 }
 
 struct Lease {
@@ -300,6 +323,16 @@ void trivial_report(rsx_report *rep) {
 
 } // namespace
 
+int rank_mode() {
+	const int o = g_rank_override.load(std::memory_order_relaxed);
+	if (o == RANK_TICKET || o == RANK_BALLOT)
+		return o;
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices)
+		return RANK_BALLOT;
+	return probe_rank_mode(dev);
+}
+
 // ---- launch glue declared in rsx_internal.cuh --------------------------------------------------
 PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes) {
 	PassGeometry g{};
@@ -376,6 +409,14 @@ int rsx_set_option(const char *name, long value) {
 		g_profile.store(value ? 1 : 0);
 		return RSX_OK;
 	}
+	if (name && strcmp(name, "rank_mode") == 0) { // -1 auto (probe), 0 ticket, 1 ballot
+		if (value < -1 || value > 1)
+			return RSX_ERR_INVALID;
+		g_rank_override.store((int)value);
+		return RSX_OK;
+	}
+	if (name && strcmp(name, "query_rank_mode") == 0)
+		return rank_mode(); // 0 ticket, 1 ballot
 	return RSX_ERR_INVALID;
 }
 

@@ -93,6 +93,9 @@ cudaError_t launch_iota_if_early(void *index_buffer, int idx_bytes, size_t n, co
 cudaError_t launch_narrow_index(const uint32_t *wide0, const uint32_t *wide1, void *index_buffer,
                                 int idx_bytes, size_t n, const Ctl *ctl, cudaStream_t st);
 
+// hardware probe for the ticket ranking (see rsx_scatter.cuh); *d_mismatch must be zeroed
+cudaError_t launch_ticket_probe(unsigned long long *d_mismatch, int num_sms, cudaStream_t st);
+
 // bench / verification helpers
 cudaError_t launch_fill(void *dst, size_t count, int key_bytes, uint64_t seed, uint64_t start,
                         int dist, uint64_t mask, uint64_t orv, cudaStream_t st);

@@ -16,8 +16,18 @@
 // Tile pipeline (persistent CTAs, tiles handed out by an atomic ticket so that a tile's
 // predecessors are always owned by running CTAs -> the look-back cannot deadlock):
 //   1. coalesced warp-striped load of the tile into registers; KDF folded into digit_of()
-//   2. per warp, per item: match_any on the digit -> peers; the group leader bumps the warp's
-//      private digit counter (shared memory) and broadcasts the old value
+//   2. per warp, per item: stable rank of the record among the warp's records with the same
+//      digit.  Two implementations (template RANK):
+//        RANK_TICKET  rank = atomicAdd(&warp_counter[digit], 1): ONE shared-memory instruction
+//                     per key.  Stable because this hardware hands out same-address tickets of
+//                     one warp instruction in ascending lane order and applies a warp's
+//                     back-to-back atomics in program order -- verified per device at first use
+//                     by ticket_probe_kernel (and offline by tools/probe_atoms.cu); if the probe
+//                     ever disagreed the library would use RANK_BALLOT.
+//        RANK_BALLOT  8 votes -> peer mask; the group leader bumps the warp counter and
+//                     broadcasts the old value.  Provably stable, ~2.5x cheaper on B200 than
+//                     __match_any_sync on 8 random bits (tools/yardstick.cu: 24 vs 60 clk/SM per
+//                     32 keys), but still above the ~13 clk/SM budget of a 70 %-of-peak pass.
 //   3. threads 0..255 (one per digit): sum / prefix the warp counters, scan the 256 tile
 //      counts, publish the tile aggregate, later walk back over predecessor tiles
 //   4. records (and payloads) are written to shared memory at their tile-sorted position
@@ -41,6 +51,9 @@ struct ScatterParams {
 	unsigned int *ticket;
 	ulonglong2 pad_rec;             // record whose derived key is all ones (tail padding)
 };
+
+// RANK_TICKET or RANK_BALLOT for the current device (probe result or rsx_set_option override).
+int rank_mode();
 
 template <typename OffT> struct StatusBits;
 template <> struct StatusBits<uint32_t> {
@@ -74,7 +87,9 @@ template <int ES, int PL, int THREADS, int ITEMS> struct ScatterSmem {
 	static constexpr size_t kBytes = kRecBytes + kPlBytes + kWhBytes + kAdjBytes + 64;
 };
 
-template <int ES, int PL, bool FLOAT, typename OffT, int THREADS, int ITEMS, int MINB>
+enum { RANK_TICKET = 0, RANK_BALLOT = 1 };
+
+template <int ES, int PL, bool FLOAT, typename OffT, int RANK, int THREADS, int ITEMS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) scatter_kernel(const ScatterParams p) {
 	using R = typename Rec<ES>::type;
 	using P = typename Payload<PL>::type;
@@ -158,16 +173,28 @@ __global__ void __launch_bounds__(THREADS, MINB) scatter_kernel(const ScatterPar
 
 		// ---- 2. rank inside the warp (stable: items ascending, lanes ascending) ----
 		uint32_t rank[ITEMS];
+		if constexpr (RANK == RANK_TICKET) {
 #pragma unroll
-		for (int i = 0; i < ITEMS; ++i) {
-			const uint32_t d = digit_of<ES, FLOAT>(rec[i], dd);
-			const uint32_t peers = __match_any_sync(FULL, d);
-			const uint32_t leader = __ffs(peers) - 1;
-			uint32_t old = 0;
-			if (lane == leader)
-				old = atomicAdd(&wh[d], (uint32_t)__popc(peers));
-			old = __shfl_sync(FULL, old, leader);
-			rank[i] = old + __popc(peers & lt);
+			for (int i = 0; i < ITEMS; ++i)
+				rank[i] = atomicAdd(&wh[digit_of<ES, FLOAT>(rec[i], dd)], 1u);
+		} else {
+#pragma unroll
+			for (int i = 0; i < ITEMS; ++i) {
+				const uint32_t d = digit_of<ES, FLOAT>(rec[i], dd);
+				uint32_t peers = FULL;
+#pragma unroll
+				for (int b = 0; b < 8; ++b) {
+					const bool bit = (d >> b) & 1u;
+					const uint32_t v = __ballot_sync(FULL, bit);
+					peers &= bit ? v : ~v;
+				}
+				const uint32_t leader = __ffs(peers) - 1;
+				uint32_t old = 0;
+				if (lane == leader)
+					old = atomicAdd(&wh[d], (uint32_t)__popc(peers));
+				old = __shfl_sync(FULL, old, leader);
+				rank[i] = old + __popc(peers & lt);
+			}
 		}
 		__syncthreads(); // (A)
 
@@ -263,14 +290,14 @@ template <int ES, int PL> struct ScatterCfg {
 	// records/thread shrink as the record + payload footprint grows (registers and smem)
 	static constexpr int kThreads = 512;
 	static constexpr int kItems = (ES + PL <= 4) ? 16 : (ES + PL <= 8) ? 12 : (ES + PL <= 16) ? 8 : 4;
-	static constexpr int kMinBlocks = 1;
+	static constexpr int kMinBlocks = (ES + PL <= 8) ? 2 : 1;
 };
 
-template <int ES, int PL, bool FLOAT, typename OffT>
-cudaError_t launch_scatter_t(const ScatterParams &sp, int num_sms, cudaStream_t st) {
+template <int ES, int PL, bool FLOAT, typename OffT, int RANK>
+cudaError_t launch_scatter_r(const ScatterParams &sp, int num_sms, cudaStream_t st) {
 	using Cfg = ScatterCfg<ES, PL>;
 	using SM = ScatterSmem<ES, PL, Cfg::kThreads, Cfg::kItems>;
-	auto kern = scatter_kernel<ES, PL, FLOAT, OffT, Cfg::kThreads, Cfg::kItems, Cfg::kMinBlocks>;
+	auto kern = scatter_kernel<ES, PL, FLOAT, OffT, RANK, Cfg::kThreads, Cfg::kItems, Cfg::kMinBlocks>;
 	static int occ_cache[64] = {}; // per device
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -291,6 +318,12 @@ cudaError_t launch_scatter_t(const ScatterParams &sp, int num_sms, cudaStream_t 
 	kern<<<grid, Cfg::kThreads, SM::kBytes, st>>>(sp);
 	count_launch();
 	return cudaGetLastError();
+}
+
+template <int ES, int PL, bool FLOAT, typename OffT>
+cudaError_t launch_scatter_t(const ScatterParams &sp, int num_sms, cudaStream_t st) {
+	return rank_mode() == RANK_TICKET ? launch_scatter_r<ES, PL, FLOAT, OffT, RANK_TICKET>(sp, num_sms, st)
+	                                  : launch_scatter_r<ES, PL, FLOAT, OffT, RANK_BALLOT>(sp, num_sms, st);
 }
 
 template <int ES, int PL>

@@ -90,6 +90,55 @@ __global__ void verify_kernel(const typename Rec<ES>::type *__restrict__ data, s
 	}
 }
 
+// Hardware probe behind RANK_TICKET (rsx_scatter.cuh): are same-address shared-memory atomicAdd
+// tickets of one warp instruction handed out in ascending lane order, and a warp's back-to-back
+// atomics applied in program order?  Compared against the ballot-derived stable rank.
+__global__ void __launch_bounds__(512) ticket_probe_kernel(unsigned long long *mismatch, int iters, uint32_t digit_mask) {
+	constexpr int ITEMS = 16;
+	__shared__ uint32_t wh[16][kBins];
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const uint32_t lt = lanemask_lt();
+	unsigned long long bad = 0;
+	for (int it = 0; it < iters; ++it) {
+		for (int b = lane; b < kBins; b += 32)
+			wh[warp][b] = 0;
+		__syncwarp();
+		uint32_t d[ITEMS], ticket[ITEMS];
+#pragma unroll
+		for (int i = 0; i < ITEMS; ++i)
+			d[i] = (uint32_t)(mix64(((unsigned long long)blockIdx.x << 40) + ((unsigned long long)it << 20) + threadIdx.x * 64 + i) >> 24) & digit_mask;
+#pragma unroll
+		for (int i = 0; i < ITEMS; ++i)
+			ticket[i] = atomicAdd(&wh[warp][d[i]], 1u);
+		__syncwarp();
+		for (int b = lane; b < kBins; b += 32)
+			wh[warp][b] = 0;
+		__syncwarp();
+#pragma unroll
+		for (int i = 0; i < ITEMS; ++i) {
+			uint32_t peers = 0xFFFFFFFFu;
+#pragma unroll
+			for (int b = 0; b < 8; ++b) {
+				const bool bit = (d[i] >> b) & 1u;
+				const uint32_t v = __ballot_sync(0xFFFFFFFFu, bit);
+				peers &= bit ? v : ~v;
+			}
+			const uint32_t leader = __ffs(peers) - 1;
+			uint32_t old = 0;
+			if (lane == leader) {
+				old = wh[warp][d[i]];
+				wh[warp][d[i]] = old + __popc(peers);
+			}
+			__syncwarp();
+			old = __shfl_sync(0xFFFFFFFFu, old, leader);
+			bad += ticket[i] != old + __popc(peers & lt);
+		}
+		__syncwarp();
+	}
+	if (bad)
+		atomicAdd(mismatch, bad);
+}
+
 inline int grid_for(size_t n, int threads, int cap) {
 	size_t g = (n + threads - 1) / threads;
 	if (g < 1) g = 1;
@@ -97,6 +146,13 @@ inline int grid_for(size_t n, int threads, int cap) {
 }
 
 } // namespace
+
+cudaError_t launch_ticket_probe(unsigned long long *d_mismatch, int num_sms, cudaStream_t st) {
+	for (uint32_t mask : {0xFFu, 0x0Fu, 0x01u, 0x00u})
+		ticket_probe_kernel<<<num_sms * 2, 512, 0, st>>>(d_mismatch, 32, mask);
+	count_launch(4);
+	return cudaGetLastError();
+}
 
 cudaError_t launch_iota_if_early(void *ib, int idx_bytes, size_t n, const Ctl *ctl, cudaStream_t st) {
 	const int g = grid_for(n, 256, 148 * 8);
