@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--rank-mode", type=int, default=-1, help="-1 auto (hardware probe), 0 ticket, 1 ballot")
+    ap.add_argument("--variant", type=int, default=0, help="scatter tuning variant (rsx_scatter.cuh)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -233,6 +234,7 @@ def main():
     rsx.reserve(rsx.workspace_bytes(n, kf.layout(kb)))
     rsx.set_profile(True)
     rsx.lib().rsx_set_option(b"rank_mode", args.rank_mode)
+    rsx.lib().rsx_set_option(b"scatter_variant", args.variant)
     rank_mode = {0: "ticket", 1: "ballot"}[rsx.lib().rsx_set_option(b"query_rank_mode", 0)]
     d0, s0, x0 = rsx.verify(pristine, kf)
 
@@ -322,7 +324,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": tname, "data": "synthetic",
         "config": {"workload": args.workload, "keys": n, "key_bytes": kb, "live_passes": passes,
-                   "dist": dname, "rank_mode": rank_mode, "l2": "inputs (n*key_bytes) larger than L2 and restored by a full-size copy before every step",
+                   "dist": dname, "rank_mode": rank_mode, "variant": args.variant, "l2": "inputs (n*key_bytes) larger than L2 and restored by a full-size copy before every step",
                    "timing": "CUDA events around each rsx_sort call on the launch stream, mean of steps",
                    "ms_min": min(times), "ms_max": max(times)},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),

@@ -323,6 +323,9 @@ void trivial_report(rsx_report *rep) {
 
 } // namespace
 
+static std::atomic<int> g_variant{0};
+int scatter_variant() { return g_variant.load(std::memory_order_relaxed); }
+
 int rank_mode() {
 	const int o = g_rank_override.load(std::memory_order_relaxed);
 	if (o == RANK_TICKET || o == RANK_BALLOT)
@@ -336,15 +339,25 @@ int rank_mode() {
 // ---- launch glue declared in rsx_internal.cuh --------------------------------------------------
 PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes) {
 	PassGeometry g{};
+	const int v = scatter_variant();
+#define GEOV(ES, PL, V)                                                                  \
+	if (record_bytes == ES && payload_bytes == PL && v == V) {                           \
+		g.threads = ScatterCfgV<ES, PL, V>::kThreads;                                    \
+		g.items = ScatterCfgV<ES, PL, V>::kItems;                                        \
+		g.smem_bytes = ScatterSmem<ES, PL, ScatterCfgV<ES, PL, V>>::kBytes;              \
+	}
 #define GEO(ES, PL)                                                                      \
 	if (record_bytes == ES && payload_bytes == PL) {                                     \
 		g.threads = ScatterCfg<ES, PL>::kThreads;                                        \
 		g.items = ScatterCfg<ES, PL>::kItems;                                            \
-		g.smem_bytes = ScatterSmem<ES, PL, ScatterCfg<ES, PL>::kThreads, ScatterCfg<ES, PL>::kItems>::kBytes; \
+		g.smem_bytes = ScatterSmem<ES, PL, ScatterCfg<ES, PL>>::kBytes;                  \
 	}
 	GEO(1, 0) GEO(1, 4) GEO(1, 8) GEO(2, 0) GEO(2, 4) GEO(2, 8) GEO(4, 0) GEO(4, 4) GEO(4, 8)
 	GEO(8, 0) GEO(8, 4) GEO(8, 8) GEO(16, 0) GEO(16, 4) GEO(16, 8)
+	GEOV(4, 0, 1) GEOV(4, 0, 2) GEOV(4, 0, 3) GEOV(4, 0, 4) GEOV(4, 0, 5)
+	GEOV(8, 0, 1) GEOV(8, 0, 2) GEOV(8, 0, 3) GEOV(8, 0, 4) GEOV(8, 0, 5)
 #undef GEO
+#undef GEOV
 	g.tile = g.threads * g.items;
 	g.ctas_per_sm = 0;
 	return g;
@@ -367,6 +380,19 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
 	sp.status = status;
 	sp.ticket = ticket;
 	sp.pad_rec = pad_record(kd);
+	sp.dbg = nullptr;
+#ifdef RSX_PHASE_TIMING
+	{
+		static unsigned long long *d_dbg = nullptr;
+		if (!d_dbg) {
+			cudaMalloc((void **)&d_dbg, 16 * sizeof(unsigned long long));
+			cudaMemset(d_dbg, 0, 16 * sizeof(unsigned long long));
+		}
+		sp.dbg = d_dbg;
+		extern unsigned long long *g_dbg_ptr;
+		g_dbg_ptr = d_dbg;
+	}
+#endif
 	const bool is_float = kd.kdf_kind == RSX_KDF_FLOAT;
 	switch (record_bytes) {
 	case 1: return launch_scatter_1(sp, payload_bytes, is_float, wide, num_sms, st);
@@ -379,6 +405,19 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
 }
 
 } // namespace rsx
+
+#ifdef RSX_PHASE_TIMING
+namespace rsx { unsigned long long *g_dbg_ptr = nullptr; }
+extern "C" int rsx_dbg_phase(unsigned long long *out16, int reset) {
+	if (!rsx::g_dbg_ptr)
+		return -1;
+	cudaDeviceSynchronize();
+	cudaMemcpy(out16, rsx::g_dbg_ptr, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+	if (reset)
+		cudaMemset(rsx::g_dbg_ptr, 0, 16 * sizeof(unsigned long long));
+	return 0;
+}
+#endif
 
 using namespace rsx;
 
@@ -413,6 +452,12 @@ int rsx_set_option(const char *name, long value) {
 		if (value < -1 || value > 1)
 			return RSX_ERR_INVALID;
 		g_rank_override.store((int)value);
+		return RSX_OK;
+	}
+	if (name && strcmp(name, "scatter_variant") == 0) { // tuning experiments, see rsx_scatter.cuh
+		if (value < 0 || value >= kNumVariants)
+			return RSX_ERR_INVALID;
+		g_variant.store((int)value);
 		return RSX_OK;
 	}
 	if (name && strcmp(name, "query_rank_mode") == 0)

@@ -50,7 +50,21 @@ struct ScatterParams {
 	void *status;                   // OffT[num_tiles][256]
 	unsigned int *ticket;
 	ulonglong2 pad_rec;             // record whose derived key is all ones (tail padding)
+	unsigned long long *dbg;        // RSX_PHASE_TIMING builds only: per-phase cycle accumulators
 };
+
+#ifdef RSX_PHASE_TIMING
+#define RSX_T(k)                                                    \
+	do {                                                            \
+		if (tid == 0) {                                             \
+			const long long now_ = clock64();                       \
+			dbg_acc[k] += (unsigned long long)(now_ - dbg_last);    \
+			dbg_last = now_;                                        \
+		}                                                           \
+	} while (0)
+#else
+#define RSX_T(k) do { } while (0)
+#endif
 
 // RANK_TICKET or RANK_BALLOT for the current device (probe result or rsx_set_option override).
 int rank_mode();
@@ -63,11 +77,47 @@ template <> struct StatusBits<unsigned long long> {
 	static constexpr unsigned long long kAgg = 1ULL << 62, kPfx = 2ULL << 62, kMask = (1ULL << 62) - 1ULL;
 };
 
-template <typename T> __device__ __forceinline__ T ld_status(const T *p) {
-	return *reinterpret_cast<const volatile T *>(p);
+// Look-back status words are self-contained messages (flag + value in one word): relaxed
+// device-scope accesses suffice, no fences.
+__device__ __forceinline__ uint32_t ld_status(const uint32_t *p) {
+	uint32_t v;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
 }
-template <typename T> __device__ __forceinline__ void st_status(T *p, T v) {
-	*reinterpret_cast<volatile T *>(p) = v;
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
+	unsigned long long v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_status(uint32_t *p, uint32_t v) {
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---- TMA 1-D bulk copy (global -> shared) completing on an mbarrier -------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+	asm volatile("{\n"
+	             ".reg .pred P1;\n"
+	             "LAB_WAIT:\n"
+	             "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+	             "@P1 bra DONE;\n"
+	             "bra LAB_WAIT;\n"
+	             "DONE:\n"
+	             "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 template <int ES> __device__ __forceinline__ typename Rec<ES>::type make_pad(const ulonglong2 &p) {
@@ -77,35 +127,76 @@ template <int ES> __device__ __forceinline__ typename Rec<ES>::type make_pad(con
 		return (typename Rec<ES>::type)p.x;
 }
 
-template <int ES, int PL, int THREADS, int ITEMS> struct ScatterSmem {
-	static constexpr int kTile = THREADS * ITEMS;
-	static constexpr int kWarps = THREADS / 32;
+// Tile geometry per (record, payload) footprint.  kStage: the next tile is prefetched by a TMA
+// bulk copy into a staging buffer while the current tile is ranked / scattered / stored.
+// V selects a tuning variant (rsx_set_option("scatter_variant", V)); V = 0 is the default.
+template <int T, int I, int MB, int LBK, bool ST> struct CfgT {
+	static constexpr int kThreads = T, kItems = I, kMinBlocks = MB, kLookback = LBK;
+	static constexpr bool kStage = ST;
+};
+// Defaults from the B200 sweeps recorded in profiles/r1_variants.md: the pass is bound by the
+// shared-memory/LSU data pipe, so the largest tile that still leaves two CTAs per SM (4-byte
+// records) or one fat CTA (wider records) wins.
+template <int ES, int PL, int V> struct ScatterCfgV
+	: CfgT<512, ((ES + PL <= 4) ? 20 : (ES + PL <= 8) ? 16 : (ES + PL <= 16) ? 8 : 4), ((ES + PL <= 4) ? 2 : 1), 16, true> {};
+constexpr int kNumVariants = 6;
+// tuning variants exist for plain 4- and 8-byte keys only
+template <> struct ScatterCfgV<4, 0, 1> : CfgT<512, 16, 2, 16, true> {};
+template <> struct ScatterCfgV<4, 0, 2> : CfgT<512, 16, 2, 8, true> {};
+template <> struct ScatterCfgV<4, 0, 3> : CfgT<1024, 16, 1, 16, true> {};
+template <> struct ScatterCfgV<4, 0, 4> : CfgT<512, 24, 1, 16, true> {};
+template <> struct ScatterCfgV<4, 0, 5> : CfgT<512, 32, 1, 16, true> {};
+template <> struct ScatterCfgV<8, 0, 1> : CfgT<512, 8, 2, 16, true> {};
+template <> struct ScatterCfgV<8, 0, 2> : CfgT<512, 10, 2, 16, true> {};
+template <> struct ScatterCfgV<8, 0, 3> : CfgT<1024, 8, 1, 16, true> {};
+template <> struct ScatterCfgV<8, 0, 4> : CfgT<512, 12, 1, 16, true> {};
+template <> struct ScatterCfgV<8, 0, 5> : CfgT<1024, 10, 1, 16, true> {};
+template <int ES, int PL> using ScatterCfg = ScatterCfgV<ES, PL, 0>;
+int scatter_variant();
+
+template <int ES, int PL, class Cfg> struct ScatterSmem {
+	static constexpr int kTile = Cfg::kThreads * Cfg::kItems;
+	static constexpr int kWarps = Cfg::kThreads / 32;
 	static constexpr size_t kRecBytes = (size_t)kTile * ES;
 	static constexpr size_t kPlBytes = (size_t)kTile * PL;
+	static constexpr size_t kStageBytes = kRecBytes + kPlBytes;
 	static constexpr size_t kWhBytes = (size_t)kWarps * kBins * 4;
 	static constexpr size_t kAdjBytes = (size_t)kBins * 8;
-	static constexpr size_t kBytes = kRecBytes + kPlBytes + kWhBytes + kAdjBytes + 64;
+	// layout: [stage rec | stage pl | sorted rec | sorted pl | warp counters | gadj | misc]
+	static constexpr size_t kOffSorted = kStageBytes;
+	static constexpr size_t kOffWh = kOffSorted + kRecBytes + kPlBytes;
+	static constexpr size_t kOffAdj = kOffWh + kWhBytes;
+	static constexpr size_t kOffLb = kOffAdj + kAdjBytes; // look-back partner partials: 256 x (8 + 4) bytes
+	static constexpr size_t kOffMisc = kOffLb + (size_t)kBins * 12;
+	static constexpr size_t kBytes = kOffMisc + 64;
 };
 
 enum { RANK_TICKET = 0, RANK_BALLOT = 1 };
 
-template <int ES, int PL, bool FLOAT, typename OffT, int RANK, int THREADS, int ITEMS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) scatter_kernel(const ScatterParams p) {
+template <int ES, int PL, bool FLOAT, typename OffT, int RANK, class Cfg>
+__global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel(const ScatterParams p) {
 	using R = typename Rec<ES>::type;
 	using P = typename Payload<PL>::type;
-	using SM = ScatterSmem<ES, PL, THREADS, ITEMS>;
+	using SM = ScatterSmem<ES, PL, Cfg>;
 	using SB = StatusBits<OffT>;
+	constexpr int THREADS = Cfg::kThreads, ITEMS = Cfg::kItems;
 	constexpr int TILE = SM::kTile;
 	constexpr int WARPS = SM::kWarps;
+	constexpr int LB = Cfg::kLookback;
 	constexpr uint32_t FULL = 0xFFFFFFFFu;
 
-	extern __shared__ __align__(16) unsigned char smem[];
-	R *s_rec = reinterpret_cast<R *>(smem);
-	P *s_pl = reinterpret_cast<P *>(smem + SM::kRecBytes);
-	uint32_t *s_wh = reinterpret_cast<uint32_t *>(smem + SM::kRecBytes + SM::kPlBytes);
-	OffT *s_gadj = reinterpret_cast<OffT *>(smem + SM::kRecBytes + SM::kPlBytes + SM::kWhBytes);
-	uint32_t *s_misc = reinterpret_cast<uint32_t *>(smem + SM::kRecBytes + SM::kPlBytes + SM::kWhBytes + SM::kAdjBytes);
-	// s_misc[0] = ticket broadcast, s_misc[1..8] = warp totals of the digit scan
+	extern __shared__ __align__(128) unsigned char smem[];
+	R *s_stage = reinterpret_cast<R *>(smem);
+	P *s_stage_pl = reinterpret_cast<P *>(smem + SM::kRecBytes);
+	R *s_rec = reinterpret_cast<R *>(smem + SM::kOffSorted);
+	P *s_pl = reinterpret_cast<P *>(smem + SM::kOffSorted + SM::kRecBytes);
+	uint32_t *s_wh = reinterpret_cast<uint32_t *>(smem + SM::kOffWh);
+	OffT *s_gadj = reinterpret_cast<OffT *>(smem + SM::kOffAdj);
+	OffT *s_lbsum = reinterpret_cast<OffT *>(smem + SM::kOffLb);
+	uint32_t *s_lbst = reinterpret_cast<uint32_t *>(smem + SM::kOffLb + (size_t)kBins * 8);
+	uint32_t *s_misc = reinterpret_cast<uint32_t *>(smem + SM::kOffMisc);
+	unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem + SM::kOffMisc + 48);
+	// s_misc[0] = next tile ticket, s_misc[1..8] = warp totals of the digit scan
 
 	// ---- pass table (device-side column skipping, radix_sort.hpp:60-70) ----
 	uint32_t ord = 0;
@@ -123,6 +214,10 @@ __global__ void __launch_bounds__(THREADS, MINB) scatter_kernel(const ScatterPar
 	P *__restrict__ pout = static_cast<P *>(p.pb.pl_buf[ord & 1]);
 	const bool synth = PL != 0 && ord == 0 && p.pb.synth_index;
 	const bool write_rec = !(last && p.pb.skip_last_rec);
+	const bool stage_pl = PL != 0 && !synth;
+	// TMA needs 16-byte aligned global addresses; tiles are multiples of 16 bytes
+	const bool can_stage = (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+	                       (!stage_pl || (reinterpret_cast<uintptr_t>(pin) & 15) == 0);
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const uint32_t lt = lanemask_lt();
@@ -130,57 +225,80 @@ __global__ void __launch_bounds__(THREADS, MINB) scatter_kernel(const ScatterPar
 	uint32_t *wh = s_wh + warp * kBins;
 	OffT *status = static_cast<OffT *>(p.status);
 	const R pad = make_pad<ES>(p.pad_rec);
+	const uint32_t full_tiles = (uint32_t)(p.n / TILE); // tiles [0, full_tiles) are complete
 
-	for (;;) {
-		if (tid == 0)
-			s_misc[0] = atomicAdd(p.ticket, 1u);
-		__syncthreads(); // (E) also fences the previous tile's reads of s_rec / s_wh
-		const uint32_t tile = s_misc[0];
-		if (tile >= p.num_tiles)
-			break;
-		const size_t base = (size_t)tile * TILE;
-		const size_t left = p.n - base;
-		const uint32_t valid = left < (size_t)TILE ? (uint32_t)left : (uint32_t)TILE;
-		const bool full = valid == (uint32_t)TILE;
-
-		// ---- 1. load (warp-striped: item i of lane l is record warp*ITEMS*32 + i*32 + l) ----
-		R rec[ITEMS];
-		P pl[PL ? ITEMS : 1];
-		const uint32_t t0 = warp * (ITEMS * 32) + lane;
-		if (full) {
-#pragma unroll
-			for (int i = 0; i < ITEMS; ++i)
-				rec[i] = __ldg(in + base + t0 + i * 32);
-		} else {
-#pragma unroll
-			for (int i = 0; i < ITEMS; ++i)
-				rec[i] = (t0 + i * 32 < valid) ? __ldg(in + base + t0 + i * 32) : pad;
-		}
+	auto prefetch = [&](uint32_t t) { // one thread
+		const size_t base = (size_t)t * TILE;
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		mbar_expect_tx(s_bar, (uint32_t)(SM::kRecBytes + (stage_pl ? SM::kPlBytes : 0)));
+		bulk_g2s(s_stage, in + base, (uint32_t)SM::kRecBytes, s_bar);
 		if constexpr (PL != 0) {
+			if (stage_pl)
+				bulk_g2s(s_stage_pl, pin + base, (uint32_t)SM::kPlBytes, s_bar);
+		}
+	};
+
+	// Tile tickets.  A ticket is claimed as late as possible -- right before the previous tile's
+	// write-out -- because every later tile's look-back has to wait for this tile's aggregate:
+	// claiming earlier (e.g. to prefetch sooner) makes successors queue up behind an idle claim.
+	if (tid == 0) {
+		mbar_init(s_bar, 1);
+		const uint32_t t = atomicAdd(p.ticket, 1u);
+		s_misc[0] = t;
+		if (can_stage && t < full_tiles)
+			prefetch(t);
+	}
+	__syncthreads();
+	uint32_t tile = s_misc[0];
+	uint32_t phase = 0;
+#ifdef RSX_PHASE_TIMING
+	unsigned long long dbg_acc[12] = {};
+	long long dbg_last = clock64();
+#endif
+
+	while (tile < p.num_tiles) {
+		RSX_T(9);
+		const size_t base = (size_t)tile * TILE;
+		const bool full = tile < full_tiles;
+		const uint32_t valid = full ? (uint32_t)TILE : (uint32_t)(p.n - base);
+		const bool staged = can_stage && full;
+
+		// ---- 1. tile -> staging buffer (warp-striped ownership: item i of lane l is record
+		//         warp*ITEMS*32 + i*32 + l).  Normally the TMA prefetch already put it there. ----
+		const uint32_t t0 = warp * (ITEMS * 32) + lane;
+		{
+			uint4 *z = reinterpret_cast<uint4 *>(wh);
+			z[lane] = make_uint4(0, 0, 0, 0);
+			z[lane + 32] = make_uint4(0, 0, 0, 0);
+		}
+		if (staged) {
+			mbar_wait(s_bar, phase);
+			phase ^= 1u;
+		} else {
+			// unaligned input or the partial last tile: plain loads, parked in the same buffer
 #pragma unroll
 			for (int i = 0; i < ITEMS; ++i) {
 				const uint32_t t = t0 + i * 32;
-				if (synth)
-					pl[i] = (P)(base + t);
-				else
-					pl[i] = (t < valid) ? __ldg(pin + base + t) : (P)0;
+				s_stage[t] = (t < valid) ? __ldg(in + base + t) : pad;
+				if constexpr (PL != 0) {
+					if (!synth)
+						s_stage_pl[t] = (t < valid) ? __ldg(pin + base + t) : (P)0;
+				}
 			}
 		}
-#pragma unroll
-		for (int b = lane; b < kBins; b += 32)
-			wh[b] = 0;
 		__syncwarp();
+		RSX_T(0);
 
 		// ---- 2. rank inside the warp (stable: items ascending, lanes ascending) ----
 		uint32_t rank[ITEMS];
 		if constexpr (RANK == RANK_TICKET) {
 #pragma unroll
 			for (int i = 0; i < ITEMS; ++i)
-				rank[i] = atomicAdd(&wh[digit_of<ES, FLOAT>(rec[i], dd)], 1u);
+				rank[i] = atomicAdd(&wh[digit_of<ES, FLOAT>(s_stage[t0 + i * 32], dd)], 1u);
 		} else {
 #pragma unroll
 			for (int i = 0; i < ITEMS; ++i) {
-				const uint32_t d = digit_of<ES, FLOAT>(rec[i], dd);
+				const uint32_t d = digit_of<ES, FLOAT>(s_stage[t0 + i * 32], dd);
 				uint32_t peers = FULL;
 #pragma unroll
 				for (int b = 0; b < 8; ++b) {
@@ -196,7 +314,9 @@ __global__ void __launch_bounds__(THREADS, MINB) scatter_kernel(const ScatterPar
 				rank[i] = old + __popc(peers & lt);
 			}
 		}
-		__syncthreads(); // (A)
+		RSX_T(1);
+		__syncthreads(); // (A) all warp counters final
+		RSX_T(2);
 
 		// ---- 3a. digit threads: warp prefixes, tile scan, publish aggregate ----
 		uint32_t tcount = 0, tstart = 0;
@@ -208,6 +328,9 @@ __global__ void __launch_bounds__(THREADS, MINB) scatter_kernel(const ScatterPar
 #pragma unroll
 			for (int w = 0; w < WARPS; ++w)
 				tcount += c[w];
+			// tail padding sorts last (digit 255, after every real record): not part of the aggregate
+			const uint32_t agg = (!full && tid == kBins - 1) ? tcount - ((uint32_t)TILE - valid) : tcount;
+			st_status(&status[(size_t)tile * kBins + tid], (OffT)((tile == 0 ? SB::kPfx : SB::kAgg) | (OffT)agg));
 			// exclusive scan of tcount over the 256 digit threads (8 warps)
 			uint32_t x = tcount;
 #pragma unroll
@@ -230,74 +353,151 @@ __global__ void __launch_bounds__(THREADS, MINB) scatter_kernel(const ScatterPar
 				s_wh[w * kBins + tid] = run;
 				run += c[w];
 			}
-			// tail padding sorts last (digit 255, after every real record): drop it from the count
-			if (!full && tid == kBins - 1)
-				tcount -= (uint32_t)TILE - valid;
-			st_status(&status[(size_t)tile * kBins + tid],
-			          (OffT)((tile == 0 ? SB::kPfx : SB::kAgg) | (OffT)tcount));
+			tcount = agg;
 		}
+		RSX_T(3);
 		__syncthreads(); // (C)
+		RSX_T(4);
 
 		// ---- 4. records / payloads to their tile-sorted slot ----
 #pragma unroll
 		for (int i = 0; i < ITEMS; ++i) {
-			const uint32_t d = digit_of<ES, FLOAT>(rec[i], dd);
-			const uint32_t pos = wh[d] + rank[i];
-			s_rec[pos] = rec[i];
+			const R r = s_stage[t0 + i * 32];
+			const uint32_t pos = wh[digit_of<ES, FLOAT>(r, dd)] + rank[i];
+			s_rec[pos] = r;
 			if constexpr (PL != 0)
-				s_pl[pos] = pl[i];
+				s_pl[pos] = synth ? (P)(base + t0 + i * 32) : s_stage_pl[t0 + i * 32];
 		}
+		RSX_T(5);
 
-		// ---- 3b. decoupled look-back, one chain per digit ----
-		if (tid < kBins) {
-			OffT excl = 0;
-			if (tile != 0) {
-				size_t q = (size_t)(tile - 1) * kBins + tid;
-				for (;;) {
-					const OffT w = ld_status(&status[q]);
-					if ((w & ~SB::kMask) == 0)
-						continue; // predecessor has not published yet
-					excl += w & SB::kMask;
-					if (w & SB::kPfx)
-						break;
-					q -= kBins;
+		// ---- 3b. decoupled look-back, one chain per digit.  The first round is split over two
+		//      threads per digit (warp w and warp w+8), so 2*LB predecessors cost one L2 round trip;
+		//      whatever is still unresolved afterwards is walked serially by the digit thread. ----
+		{
+			constexpr bool kPair = THREADS >= 2 * kBins;
+			const uint32_t dgt = tid & (kBins - 1), half = tid / kBins;
+			OffT part = 0;
+			uint32_t st = 0, used = 0; // st: 0 = only aggregates so far, 1 = reached a prefix, 2 = hit an unpublished word
+			if (half < (kPair ? 2u : 1u)) {
+				const int q = (int)tile - 1 - (int)half * LB;
+				OffT w[LB];
+#pragma unroll
+				for (int j = 0; j < LB; ++j)
+					w[j] = (q - j >= 0) ? ld_status(&status[(size_t)(q - j) * kBins + dgt]) : (OffT)SB::kPfx;
+#pragma unroll
+				for (int j = 0; j < LB; ++j) {
+					if (st == 0) {
+						if ((w[j] & ~SB::kMask) == 0) {
+							st = 2;
+						} else {
+							part += w[j] & SB::kMask;
+							++used;
+							if (w[j] & SB::kPfx)
+								st = 1;
+						}
+					}
 				}
-				st_status(&status[(size_t)tile * kBins + tid], (OffT)(SB::kPfx | (excl + (OffT)tcount)));
 			}
-			s_gadj[tid] = (OffT)p.offs[tid] + excl - (OffT)tstart;
+			if constexpr (kPair) {
+				if (half == 1) {
+					s_lbsum[dgt] = part;
+					s_lbst[dgt] = st;
+					asm volatile("bar.arrive %0, 64;" ::"r"(2 + (warp & 7)) : "memory");
+				}
+			}
+			if (half == 0) {
+				OffT excl = part;
+				bool done = st == 1;
+				int q = (int)tile - 1 - (int)used;
+				if constexpr (kPair) {
+					asm volatile("bar.sync %0, 64;" ::"r"(2 + warp) : "memory");
+					if (st == 0) { // own window was all aggregates: splice the partner's window
+						const uint32_t pst = s_lbst[dgt];
+						if (pst != 2) {
+							excl += s_lbsum[dgt];
+							q -= LB;
+							done = pst == 1;
+						}
+					}
+				}
+				while (!done) { // rare: long chains and unpublished predecessors
+#ifdef RSX_PHASE_TIMING
+					if (tid == 0) dbg_acc[10] += 1;
+#endif
+					OffT w[LB];
+#pragma unroll
+					for (int j = 0; j < LB; ++j)
+						w[j] = (q - j >= 0) ? ld_status(&status[(size_t)(q - j) * kBins + dgt]) : (OffT)SB::kPfx;
+#pragma unroll
+					for (int j = 0; j < LB; ++j) {
+						if (!done) {
+							OffT v = w[j];
+							while ((v & ~SB::kMask) == 0) { // not published yet: poll this one word, politely
+#ifdef RSX_PHASE_TIMING
+								if (tid == 0) dbg_acc[11] += 1;
+#endif
+								__nanosleep(40);
+								v = ld_status(&status[(size_t)(q - j) * kBins + dgt]);
+							}
+							excl += v & SB::kMask;
+							done = (v & SB::kPfx) != 0;
+						}
+					}
+					q -= LB;
+				}
+				if (tile != 0)
+					st_status(&status[(size_t)tile * kBins + dgt], (OffT)(SB::kPfx | (excl + (OffT)tcount)));
+				s_gadj[dgt] = (OffT)p.offs[dgt] + excl - (OffT)tstart;
+			}
 		}
-		__syncthreads(); // (D)
+		RSX_T(6);
+		if (tid == 0) // next ticket: claimed as late as possible (see above)
+			s_misc[0] = atomicAdd(p.ticket, 1u);
+		__syncthreads(); // (D) sorted tile + gadj complete; nobody reads the staging buffer any more
+		const uint32_t next_tile = s_misc[0];
+		if (tid == 0 && can_stage && next_tile < full_tiles)
+			prefetch(next_tile); // TMA: lands while this tile is being stored
+		RSX_T(7);
 
 		// ---- 5. coalesced per-bucket stores ----
+		if (full) {
 #pragma unroll
-		for (int i = 0; i < ITEMS; ++i) {
-			const uint32_t s = tid + i * THREADS;
-			if (full || s < valid) {
+			for (int i = 0; i < ITEMS; ++i) {
+				const uint32_t s = tid + i * THREADS;
 				const R r = s_rec[s];
-				const uint32_t d = digit_of<ES, FLOAT>(r, dd);
-				const OffT g = s_gadj[d] + (OffT)s;
+				const OffT g = s_gadj[digit_of<ES, FLOAT>(r, dd)] + (OffT)s;
+				if (write_rec)
+					out[g] = r;
+				if constexpr (PL != 0)
+					pout[g] = s_pl[s];
+			}
+		} else {
+			for (uint32_t s = tid; s < valid; s += THREADS) {
+				const R r = s_rec[s];
+				const OffT g = s_gadj[digit_of<ES, FLOAT>(r, dd)] + (OffT)s;
 				if (write_rec)
 					out[g] = r;
 				if constexpr (PL != 0)
 					pout[g] = s_pl[s];
 			}
 		}
+		RSX_T(8);
+		tile = next_tile;
+		// the next iteration rewrites wh (read in step 4, fenced by D) and s_rec (fenced by A', C')
 	}
+#ifdef RSX_PHASE_TIMING
+	if (tid == 0 && p.dbg) {
+		for (int k = 0; k < 12; ++k)
+			atomicAdd(&p.dbg[k], dbg_acc[k]);
+		atomicAdd(&p.dbg[12], 1ULL);
+	}
+#endif
 }
 
-// ---- geometry ---------------------------------------------------------------------------------
-template <int ES, int PL> struct ScatterCfg {
-	// records/thread shrink as the record + payload footprint grows (registers and smem)
-	static constexpr int kThreads = 512;
-	static constexpr int kItems = (ES + PL <= 4) ? 16 : (ES + PL <= 8) ? 12 : (ES + PL <= 16) ? 8 : 4;
-	static constexpr int kMinBlocks = (ES + PL <= 8) ? 2 : 1;
-};
-
-template <int ES, int PL, bool FLOAT, typename OffT, int RANK>
-cudaError_t launch_scatter_r(const ScatterParams &sp, int num_sms, cudaStream_t st) {
-	using Cfg = ScatterCfg<ES, PL>;
-	using SM = ScatterSmem<ES, PL, Cfg::kThreads, Cfg::kItems>;
-	auto kern = scatter_kernel<ES, PL, FLOAT, OffT, RANK, Cfg::kThreads, Cfg::kItems, Cfg::kMinBlocks>;
+template <int ES, int PL, bool FLOAT, typename OffT, int RANK, class Cfg>
+cudaError_t launch_scatter_c(const ScatterParams &sp, int num_sms, cudaStream_t st) {
+	using SM = ScatterSmem<ES, PL, Cfg>;
+	auto kern = scatter_kernel<ES, PL, FLOAT, OffT, RANK, Cfg>;
 	static int occ_cache[64] = {}; // per device
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -312,12 +512,29 @@ cudaError_t launch_scatter_r(const ScatterParams &sp, int num_sms, cudaStream_t 
 			return e;
 		ctas_per_sm = occ > 0 ? occ : 1;
 	}
+	ScatterParams q = sp;
+	q.num_tiles = (uint32_t)((sp.n + SM::kTile - 1) / SM::kTile); // status rows are sized for the default tile (the smallest)
 	uint32_t grid = (uint32_t)num_sms * (uint32_t)ctas_per_sm;
-	if (grid > sp.num_tiles)
-		grid = sp.num_tiles;
-	kern<<<grid, Cfg::kThreads, SM::kBytes, st>>>(sp);
+	if (grid > q.num_tiles)
+		grid = q.num_tiles;
+	kern<<<grid, Cfg::kThreads, SM::kBytes, st>>>(q);
 	count_launch();
 	return cudaGetLastError();
+}
+
+template <int ES, int PL, bool FLOAT, typename OffT, int RANK>
+cudaError_t launch_scatter_r(const ScatterParams &sp, int num_sms, cudaStream_t st) {
+	if constexpr ((ES == 4 || ES == 8) && PL == 0 && !FLOAT && RANK == RANK_TICKET && sizeof(OffT) == 4) {
+		switch (scatter_variant()) {
+		case 1: return launch_scatter_c<ES, PL, FLOAT, OffT, RANK, ScatterCfgV<ES, PL, 1>>(sp, num_sms, st);
+		case 2: return launch_scatter_c<ES, PL, FLOAT, OffT, RANK, ScatterCfgV<ES, PL, 2>>(sp, num_sms, st);
+		case 3: return launch_scatter_c<ES, PL, FLOAT, OffT, RANK, ScatterCfgV<ES, PL, 3>>(sp, num_sms, st);
+		case 4: return launch_scatter_c<ES, PL, FLOAT, OffT, RANK, ScatterCfgV<ES, PL, 4>>(sp, num_sms, st);
+		case 5: return launch_scatter_c<ES, PL, FLOAT, OffT, RANK, ScatterCfgV<ES, PL, 5>>(sp, num_sms, st);
+		default: break;
+		}
+	}
+	return launch_scatter_c<ES, PL, FLOAT, OffT, RANK, ScatterCfg<ES, PL>>(sp, num_sms, st);
 }
 
 template <int ES, int PL, bool FLOAT, typename OffT>
