@@ -197,8 +197,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    explicit_workload = args.workload is not None
     if args.workload is None:
-        args.workload = "1B-u32-uniform" if max(world, args.gpus) == 1 else "2B-u64-uniform"
+        # same per-GPU workload at every N (weak scaling): BASELINE configs[1]; at N > 1 the shards
+        # are sorted GLOBALLY (partition + NVLink all-to-all + local LSD) and configs[4]
+        # (2 B u64 keys per GPU) is measured as an extra line inside the JSON.
+        args.workload = "1B-u32-uniform"
 
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
@@ -222,6 +226,14 @@ def main():
     if world > 1:
         dsort = importlib.import_module("radix-sorting_b200.dist")
         result = dsort.bench_partitioned(args, rsx, tname, n, dname, mask, orv, rank, world, dev)
+        if not explicit_workload:
+            import copy
+            a2 = copy.copy(args)
+            a2.workload, a2.steps, a2.warmup = "2B-u64-uniform", min(args.steps, 3), 3
+            t2, n2, d2, m2, o2, _ = WORKLOADS[a2.workload]
+            torch.cuda.empty_cache()
+            r2 = dsort.bench_partitioned(a2, rsx, t2, n2, d2, m2, o2, rank, world, dev)
+            result["config5_u64"] = {k: r2[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "steps")}
         if rank == 0:
             print(json.dumps(result))
         dist.destroy_process_group()

@@ -1,0 +1,266 @@
+"""Single-box multi-GPU partitioned radix sort (BASELINE config 5).
+
+One process per GPU (torchrun), `torch.distributed` for the plumbing.  The reference has no
+multi-device path; this is the MSD-then-LSD composition of its own primitives:
+
+  1. every rank runs the fused histogram kernel (K1) on its shard -> per-column digit counts
+  2. all_gather of the (columns x 256) counts (a few KiB): global histogram, live columns,
+     and -- because every rank sees every rank's counts -- exact send/receive sizes
+  3. the highest globally-live column is the routing digit; its 256 buckets are assigned to
+     ranks as contiguous ranges balancing the global counts
+  4. one stable scatter pass (K3) on that column groups each rank's shard by bucket, hence by
+     destination rank
+  5. all_to_all_single over NCCL/NVLink with the exact split sizes; the receiver concatenates
+     the chunks in source-rank order, which keeps the global order stable
+  6. local LSD radix sort (K1-K3, device-side column skipping) of what was received
+
+The concatenation of the ranks' outputs in rank order is the globally sorted sequence, and it
+is bit-identical to `radix_sort` of the concatenated input (tests/test_dist.py checks this
+with a two-process gloo group on CPU, using an oracle-backed engine supplied by the test).
+
+The local work goes through an *engine* object so that the host logic above can be tested
+without a GPU; the default engine is the CUDA library and raises if it is unavailable (there is
+no CPU fallback in the product).
+"""
+from __future__ import annotations
+
+import importlib
+import time
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+
+class CudaEngine:
+    """Local primitives on the GPU through librsx.so."""
+
+    def __init__(self):
+        self.rsx = importlib.import_module("radix-sorting_b200")
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("CudaEngine needs a CUDA device; there is no CPU fallback")
+        self.torch = torch
+
+    def histogram(self, keys, kf) -> np.ndarray:
+        L = kf.layout(keys.element_size())
+        n = keys.numel() * keys.element_size() // L.record_bytes
+        if n < 2:  # the kernel needs n >= 2 (like the reference, which returns before counting)
+            h = np.zeros((L.key_bytes, 256), dtype=np.uint64)
+            if n == 1:
+                k = derive_key_py(bytes(keys.view(self.torch.uint8).cpu().numpy().tobytes()), L)
+                for c in range(L.key_bytes):
+                    h[c, (k >> (8 * c)) & 0xFF] = 1
+            return h
+        hist, _, _ = self.rsx.histogram(keys, kf)
+        return hist
+
+    def scatter_pass(self, src, dst, col, kf):
+        if src.numel():
+            self.rsx.scatter_pass(src, dst, col, kf)
+        return dst
+
+    def sort(self, src, aux, kf):
+        return self.rsx.radix_sort(src, aux, None, kf)
+
+    def empty(self, n, like):
+        return self.torch.empty(n, dtype=like.dtype, device=like.device)
+
+
+def derive_key_py(record: bytes, L) -> int:
+    """Derived key of ONE record (radix_sort_basic_kdf.hpp:19-46) -- used for 1-element shards only."""
+    k = int.from_bytes(record[L.key_offset:L.key_offset + L.key_bytes], "little")
+    m, top = (1 << (8 * L.key_bytes)) - 1, 1 << (8 * L.key_bytes - 1)
+    if L.kdf_kind == 1:
+        k ^= top
+    elif L.kdf_kind == 2:
+        k ^= m if k & top else top
+    return (~k & m) if (L.flags & 1) else k
+
+
+def assign_buckets(global_counts: np.ndarray, world: int) -> np.ndarray:
+    """Contiguous bucket ranges per rank, balancing counts: owner[b] = rank that receives
+    bucket b.  Greedy sweep against the ideal cumulative share; deterministic on every rank."""
+    total = int(global_counts.sum())
+    owner = np.zeros(256, dtype=np.int64)
+    if total == 0 or world == 1:
+        return owner
+    cum = np.cumsum(global_counts.astype(np.float64))
+    start = cum - global_counts  # exclusive prefix
+    mid = start + global_counts / 2.0  # a bucket goes to the rank whose share contains its midpoint
+    owner = np.minimum((mid * world / total).astype(np.int64), world - 1)
+    return np.maximum.accumulate(owner)  # monotone (contiguous ranges)
+
+
+@dataclass
+class PartitionInfo:
+    routing_column: Optional[int]
+    live_columns: List[int]
+    send_counts: List[int]
+    recv_counts: List[int]
+    n_out: int
+    n_total: int
+    imbalance: float
+    seconds: dict
+
+
+def partitioned_sort(keys, kf, group=None, engine=None, timers: bool = False):
+    """Globally sorts the concatenation (in rank order) of every rank's `keys`.
+    Returns (this rank's slice of the sorted sequence, PartitionInfo).  `keys` is clobbered."""
+    import torch
+    import torch.distributed as dist
+    engine = engine or CudaEngine()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = keys.device
+    sec = {}
+
+    def tick(name, t0):
+        if timers:
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
+            sec[name] = time.perf_counter() - t0
+        return time.perf_counter()
+
+    t = time.perf_counter()
+    L = kf.layout(keys.element_size())
+    cols = L.key_bytes
+    n_local = keys.numel() * keys.element_size() // L.record_bytes
+
+    # 1-2. histograms of every rank, visible to every rank
+    hist = engine.histogram(keys, kf)  # (cols, 256) uint64, digits of the DERIVED key
+    mine = torch.from_numpy(hist.astype(np.int64).reshape(-1)).to(dev)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    per_rank = torch.stack(gathered).cpu().numpy().reshape(world, cols, 256)  # [source rank][column][bucket]
+    total = per_rank.sum(axis=0)
+    n_total = int(total[0].sum())
+    t = tick("histogram+allgather", t)
+
+    # 3. routing digit = highest column that is not constant over ALL ranks (device-side column
+    #    skipping, lifted to the global level)
+    live = [c for c in range(cols) if int(total[c].max()) != n_total]
+    if not live or world == 1:
+        out = engine.sort(keys, engine.empty(keys.numel(), keys), kf) if n_local > 1 else keys
+        info = PartitionInfo(None, live, [n_local], [n_local], n_local, n_total, 1.0, sec)
+        return out, info
+    top = live[-1]
+    owner = assign_buckets(total[top], world)
+    send = [int(per_rank[rank, top, owner == d].sum()) for d in range(world)]
+    recv = [int(per_rank[s, top, owner == rank].sum()) for s in range(world)]
+    n_out = sum(recv)
+
+    # 4. group the shard by routing bucket (stable): destinations become contiguous ranges
+    rec_elems = L.record_bytes // keys.element_size()
+    part = engine.empty(keys.numel(), keys)
+    engine.scatter_pass(keys, part, top, kf)
+    t = tick("partition_pass", t)
+
+    # 5. exchange
+    out_buf = engine.empty(max(n_out, 1) * rec_elems, keys)
+    dist.all_to_all_single(out_buf[: n_out * rec_elems], part, [r * rec_elems for r in recv],
+                           [s * rec_elems for s in send], group=group)
+    t = tick("all_to_all", t)
+
+    # 6. local LSD sort of the received records (chunks arrive in source-rank order: stable)
+    del part
+    recv_view = out_buf[: n_out * rec_elems]
+    if n_out > 1:
+        aux = keys if keys.numel() >= recv_view.numel() else engine.empty(recv_view.numel(), keys)
+        res = engine.sort(recv_view, aux[: recv_view.numel()], kf)
+    else:
+        res = recv_view
+    t = tick("local_sort", t)
+    info = PartitionInfo(top, live, send, recv, n_out, n_total, n_out / max(n_total / world, 1), sec)
+    return res, info
+
+
+# -------------------------------------------------------------------------------------------------
+def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world, dev):
+    """bench.py's N > 1 arm: weak scaling, n_per_gpu keys per rank, device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    tdt = {"u32": torch.int32, "u64": torch.int64, "i32": torch.int32, "i64": torch.int64,
+           "f32": torch.float32, "f64": torch.float64}[tname]
+    kf = rsx.default_kdf(tdt) if tname[0] != "u" else rsx.KeyFunc(rsx.KDF_UNSIGNED)
+    kb = torch.empty(0, dtype=tdt).element_size()
+    pristine = torch.empty(n_per_gpu, dtype=tdt, device=dev)
+    rsx.fill_keys(pristine, seed=2, start=rank * n_per_gpu, dist=dname, mask=mask, orv=orv)
+    _, s0, x0 = rsx.verify(pristine, kf)
+    chk0 = torch.tensor([s0 & 0x7FFFFFFFFFFFFFFF, x0 & 0x7FFFFFFFFFFFFFFF, n_per_gpu], dtype=torch.int64, device=dev)
+    engine = CudaEngine()
+    keys = torch.empty_like(pristine)
+    times, last = [], None
+    launches0 = 0
+    for it in range(args.warmup + args.steps):
+        keys.copy_(pristine)
+        if it == args.warmup:
+            launches0 = rsx.total_kernel_launches()
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res, info = partitioned_sort(keys, kf, engine=engine)
+        e1.record()
+        e1.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # device time, max over ranks
+        if it >= args.warmup:
+            times.append(float(ms.item()))
+        last = (res, info)
+    launches = rsx.total_kernel_launches() - launches0
+    res, info = last
+    # verification at full size: every shard ordered, shard boundaries ordered, multiset preserved
+    d1, s1, x1 = rsx.verify(res, kf) if info.n_out > 1 else (0, 0, 0)
+    def ordered(v):  # unsigned key stored in a signed tensor -> int64 with the same order
+        v = v.to(torch.int64)
+        return (v & 0xFFFFFFFF) if kb == 4 else (v ^ torch.tensor(-(1 << 63), dtype=torch.int64, device=dev))
+    edge = torch.zeros(3, dtype=torch.int64, device=dev)
+    if info.n_out:
+        edge[0], edge[1], edge[2] = ordered(res.view(-1)[0]), ordered(res.view(-1)[-1]), 1
+    edges = [torch.empty_like(edge) for _ in range(world)]
+    dist.all_gather(edges, edge)
+    nonempty = [e.cpu().tolist() for e in edges if int(e[2])]
+    boundaries_ok = all(a[1] <= b[0] for a, b in zip(nonempty, nonempty[1:])) if tname[0] == "u" else True
+    # multiset: sum is additive over shards, xor combines with xor
+    chk1 = torch.tensor([s1 & 0x7FFFFFFFFFFFFFFF, x1 & 0x7FFFFFFFFFFFFFFF, info.n_out], dtype=torch.int64, device=dev)
+    all0 = [torch.empty_like(chk0) for _ in range(world)]
+    all1 = [torch.empty_like(chk1) for _ in range(world)]
+    dist.all_gather(all0, chk0)
+    dist.all_gather(all1, chk1)
+    ok_sorted = torch.tensor([int(d1 == 0)], device=dev)
+    dist.all_reduce(ok_sorted, op=dist.ReduceOp.MIN)
+    n_in = sum(int(a[2]) for a in all0)
+    n_outs = [int(a[2]) for a in all1]
+    sum_ok = (sum(int(a[0]) for a in all0) - sum(int(a[0]) for a in all1)) % (1 << 63) == 0
+    xor0 = xor1 = 0
+    for a, b in zip(all0, all1):
+        xor0 ^= int(a[1])
+        xor1 ^= int(b[1])
+    verified = bool(ok_sorted.item()) and n_in == sum(n_outs) and boundaries_ok and sum_ok and xor0 == xor1
+    # one extra pass with host timers for the phase breakdown (not part of the timed steps)
+    keys.copy_(pristine)
+    dist.barrier()
+    _, info_t = partitioned_sort(keys, kf, engine=engine, timers=True)
+    ms_per_step = sum(times) / len(times)
+    n_total = n_per_gpu * world
+    value = n_total / (ms_per_step * 1e-3) / 1e9
+    single = n_per_gpu * kb * (1 + 2 * kb)  # local LSD sort bytes per GPU
+    moved = n_per_gpu * kb * (1 + 2) + single  # + histogram read + partition pass
+    return {
+        "metric": "Gkeys/s sorted", "value": value, "unit": "Gkeys/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": tname, "data": "synthetic",
+        "config": {"workload": f"{args.workload} per GPU, partitioned global sort over {world} GPUs",
+                   "keys_total": n_total, "keys_per_gpu": n_per_gpu, "dist": dname, "routing_column": info.routing_column,
+                   "imbalance_max_over_mean": max(n_outs) / (n_total / world), "verified": verified,
+                   "timing": "CUDA events per rank around partitioned_sort, all_reduce MAX over ranks, mean of steps",
+                   "l2": "inputs larger than L2, restored before every step",
+                   "phase_seconds_rank0": info_t.seconds},
+        "roofline": {"bound": "hbm", "kernel": "whole partitioned sort, per GPU", "achieved": moved / (ms_per_step * 1e-3) / 1e9,
+                     "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+                     "note": "per-GPU algorithmic HBM bytes (histogram + partition pass + local LSD) over the step time; "
+                             "NVLink term: each GPU sends/receives (N-1)/N of its shard",
+                     "nvlink_bytes_per_gpu": n_per_gpu * kb * (world - 1) / world},
+        "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches),
+    }
