@@ -135,7 +135,9 @@ int rsx_version(void);
 uint64_t rsx_total_kernel_launches(void); /* process-wide count, for bench.py's gpu_launches */
 /* Options: "rank_mode" (-1 auto [default]: per-device hardware probe picks the one-instruction
  * ticket ranking or the ballot ranking, 0 force ticket, 1 force ballot; DESIGN.md "K3");
- * "query_rank_mode" returns the mode in effect (0 / 1).  "profile" (0/1): bracket every kernel of rsx_sort / rsx_sort_rank with CUDA events on
+ * "query_rank_mode" returns the mode in effect (0 / 1).  "scatter_variant" (0..5) selects a tile
+ * geometry used in tuning sweeps, "force_wide" (0/1) runs the n >= 2^30 (64-bit offset) kernels
+ * at any n (tests).  "profile" (0/1): bracket every kernel of rsx_sort / rsx_sort_rank with CUDA events on
  * the launch stream so that per-kernel device times can be read back with rsx_get_profile
  * (bench.py's roofline leg; off by default because the extra events perturb nothing but are
  * not free). */

@@ -19,6 +19,7 @@
 namespace rsx {
 
 static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<int> g_force_wide{0};
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 namespace {
@@ -85,6 +86,9 @@ struct DeviceState {
 	size_t ws_bytes = 0;
 	bool busy = false;
 	Ctl *pinned = nullptr; // one slot per device is enough: guarded by `busy`
+	void *stage = nullptr; // device staging for host-pointer calls (grow-only, like ws)
+	size_t stage_bytes = 0;
+	bool stage_busy = false;
 };
 constexpr int kMaxDevices = 64;
 DeviceState g_dev[kMaxDevices];
@@ -142,6 +146,48 @@ struct Lease {
 		}
 	}
 };
+
+// Device staging buffer for host-pointer calls: cached so that a drop-in caller sorting host
+// arrays repeatedly does not pay cudaMalloc/cudaFree of gigabytes on every call.
+struct StageLease {
+	int dev = -1;
+	void *ptr = nullptr;
+	bool cached = false;
+	~StageLease() {
+		if (dev < 0)
+			return;
+		if (cached) {
+			std::lock_guard<std::mutex> lk(g_dev[dev].mu);
+			g_dev[dev].stage_busy = false;
+		} else if (ptr) {
+			cudaFree(ptr);
+		}
+	}
+};
+
+int acquire_stage(StageLease &L, int dev, size_t bytes) {
+	DeviceState &D = g_dev[dev];
+	L.dev = dev;
+	std::unique_lock<std::mutex> lk(D.mu);
+	if (!D.stage_busy) {
+		if (D.stage_bytes < bytes) {
+			if (D.stage) {
+				cudaFree(D.stage);
+				D.stage = nullptr;
+				D.stage_bytes = 0;
+			}
+			CU(cudaMalloc(&D.stage, bytes));
+			D.stage_bytes = bytes;
+		}
+		D.stage_busy = true;
+		L.ptr = D.stage;
+		L.cached = true;
+		return RSX_OK;
+	}
+	lk.unlock();
+	CU(cudaMalloc(&L.ptr, bytes));
+	return RSX_OK;
+}
 
 int acquire(Lease &L, int dev, size_t bytes) {
 	DeviceState &D = g_dev[dev];
@@ -241,7 +287,7 @@ void make_plan(Plan &P, size_t n, const rsx_layout *L, const KeyDesc &kd, int ra
 	P.pl_bytes = forced_pl >= 0 ? forced_pl : rank_idx_bytes == 0 ? 0 : (rank_idx_bytes == 8 ? 8 : 4);
 	P.geo = scatter_geometry(P.rb, P.pl_bytes);
 	P.tiles = (uint32_t)((n + P.geo.tile - 1) / P.geo.tile);
-	P.wide = n >= (1ULL << 30);
+	P.wide = n >= (1ULL << 30) || g_force_wide.load(std::memory_order_relaxed);
 	P.status_bytes_per_col = (size_t)P.tiles * kBins * (P.wide ? 8 : 4);
 	size_t off = align_up(sizeof(WsHead), 256);
 	P.off_status = off;
@@ -460,6 +506,10 @@ int rsx_set_option(const char *name, long value) {
 		g_variant.store((int)value);
 		return RSX_OK;
 	}
+	if (name && strcmp(name, "force_wide") == 0) { // tests: run the n >= 2^30 (64-bit offset) kernels at small n
+		g_force_wide.store(value ? 1 : 0);
+		return RSX_OK;
+	}
 	if (name && strcmp(name, "query_rank_mode") == 0)
 		return rank_mode(); // 0 ticket, 1 ballot
 	return RSX_ERR_INVALID;
@@ -502,6 +552,11 @@ void rsx_release(void) {
 		cudaFree(D.ws);
 		D.ws = nullptr;
 		D.ws_bytes = 0;
+	}
+	if (!D.stage_busy && D.stage) {
+		cudaFree(D.stage);
+		D.stage = nullptr;
+		D.stage_bytes = 0;
 	}
 }
 
@@ -563,8 +618,10 @@ int rsx_sort(void *src, void *aux, size_t n, const rsx_layout *layout, void **re
 	// the bytes land in the buffer it would have returned, the other buffer is left as is
 	// (the reference leaves the penultimate pass there, which callers must treat as garbage).
 	const size_t bytes = n * layout->record_bytes;
-	void *d = nullptr;
-	CU(cudaMalloc(&d, 2 * align_up(bytes, 256)));
+	StageLease SL;
+	if ((r = acquire_stage(SL, dev, 2 * align_up(bytes, 256))))
+		return r;
+	void *d = SL.ptr;
 	void *dsrc = d, *daux = static_cast<unsigned char *>(d) + align_up(bytes, 256);
 	void *dres = nullptr;
 	rsx_report local;
@@ -586,7 +643,6 @@ int rsx_sort(void *src, void *aux, size_t n, const rsx_layout *layout, void **re
 	}
 	if (!r)
 		*result = rep->result_in_aux ? aux : src;
-	cudaFree(d);
 	return r;
 }
 
@@ -674,9 +730,10 @@ int rsx_sort_rank(const void *src, void *index_buffer, size_t n, const rsx_layou
 		return rank_device(src, index_buffer, n, layout, kd, idx_bytes, result, rep, st, dev, false);
 
 	const size_t sbytes = n * layout->record_bytes, ibytes = n * (size_t)idx_bytes;
-	void *d = nullptr;
-	CU(cudaMalloc(&d, align_up(sbytes, 256) + 2 * ibytes));
-	unsigned char *dsrc = static_cast<unsigned char *>(d), *dib = dsrc + align_up(sbytes, 256);
+	StageLease SL;
+	if ((r = acquire_stage(SL, dev, align_up(sbytes, 256) + 2 * ibytes)))
+		return r;
+	unsigned char *dsrc = static_cast<unsigned char *>(SL.ptr), *dib = dsrc + align_up(sbytes, 256);
 	void *dres = nullptr;
 	rsx_report local;
 	if (!rep)
@@ -698,7 +755,6 @@ int rsx_sort_rank(const void *src, void *index_buffer, size_t n, const rsx_layou
 	}
 	if (!r)
 		*result = hres;
-	cudaFree(d);
 	return r;
 }
 

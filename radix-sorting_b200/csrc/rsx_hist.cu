@@ -18,6 +18,8 @@
 //     packed two per word (128 KiB), flushed before a copy can reach 65535.
 //   * descents (kdf(a[i]) > kdf(a[i+1])) are counted on the fly: inside a thread's vector,
 //     across lanes with a shuffle, across warps with one extra scalar load by lane 31.
+#include <type_traits>
+
 #include "rsx_device.cuh"
 
 namespace rsx {
@@ -33,13 +35,58 @@ template <int KB> struct HistSmem {
 	static constexpr size_t kBytes = (size_t)kWords * 4;
 };
 
-template <int KB>
-__device__ __forceinline__ void hist_add(uint32_t *sh, uint32_t col, uint32_t digit, uint32_t lane) {
-	if constexpr (HistSmem<KB>::kPacked) {
-		// copy l and copy l+16 share a word (low / high half); word -> bank (d&1)*16 + l%16
-		atomicAdd(&sh[(col * kBins + digit) * 16u + (lane & 15u)], 1u << (lane & 16u));
-	} else {
-		atomicAdd(&sh[(col * kBins + digit) * 32u + lane], 1u);
+// Key derivation with everything data-independent folded into three uniform constants:
+//   derived = raw ^ xor_const ^ (sign(raw) ? float_mask : 0)
+// unsigned: 0 / 0, signed: top / 0, float: top / (mask ^ top); descending adds mask to xor_const.
+template <typename KT> struct KeyXform {
+	uint32_t word_sel, shift;
+	KT mask, xor_const, float_mask;
+	uint32_t sign_shift;
+};
+template <typename KT> __host__ KeyXform<KT> make_xform(const KeyDesc &kd) {
+	KeyXform<KT> x;
+	x.word_sel = kd.word_sel;
+	x.shift = kd.key_shift;
+	const unsigned long long m = kd.key_bytes >= 8 ? ~0ULL : ((1ULL << (8 * kd.key_bytes)) - 1ULL);
+	const unsigned long long top = 1ULL << (8 * kd.key_bytes - 1);
+	x.mask = (KT)m;
+	x.xor_const = (KT)((kd.kdf_kind != RSX_KDF_UNSIGNED ? top : 0ULL) ^ (kd.invert ? m : 0ULL));
+	x.float_mask = (KT)(kd.kdf_kind == RSX_KDF_FLOAT ? (m ^ top) : 0ULL);
+	x.sign_shift = 8 * kd.key_bytes - 1;
+	return x;
+}
+template <int ES, typename KT>
+__device__ __forceinline__ KT derive_fast(const typename Rec<ES>::type &r, const KeyXform<KT> &x) {
+	KT raw;
+	if constexpr (ES <= 4)
+		raw = (KT)((uint32_t)r >> x.shift);
+	else
+		raw = (KT)(key_word<ES>(r, x.word_sel) >> x.shift);
+	raw &= x.mask;
+	KT k = raw ^ x.xor_const;
+	if (x.float_mask != 0) // uniform
+		k ^= ((KT)0 - (KT)((raw >> x.sign_shift) & 1u)) & x.float_mask;
+	return k;
+}
+
+// One increment per column.  `lane_base` already contains the lane's bank offset, so each
+// digit costs a shift, a mask, an add and the shared atomic.
+template <int KB, typename KT>
+__device__ __forceinline__ void hist_one(unsigned char *lane_base, KT key, uint32_t inc) {
+	constexpr bool kPacked = HistSmem<KB>::kPacked;
+	constexpr uint32_t kColBytes = kPacked ? kBins * 64u : kBins * 128u; // bytes per column
+	constexpr uint32_t kSh = kPacked ? 6u : 7u;                          // bytes per bin = 1 << kSh
+	constexpr uint32_t kMaskOff = 0xFFu << kSh;
+#pragma unroll
+	for (int c = 0; c < KB; ++c) {
+		uint32_t half = (uint32_t)key;
+		if constexpr (sizeof(KT) == 8) {
+			if (c >= 4)
+				half = (uint32_t)(key >> 32);
+		}
+		const int cc = c & 3;
+		const uint32_t off = cc == 0 ? (half << kSh) & kMaskOff : (half >> (8 * cc - kSh)) & kMaskOff;
+		atomicAdd(reinterpret_cast<uint32_t *>(lane_base + c * kColBytes + off), inc);
 	}
 }
 
@@ -67,18 +114,12 @@ __device__ __forceinline__ void hist_flush(uint32_t *sh, unsigned long long *ghi
 }
 
 template <int ES, int KB>
-__device__ __forceinline__ void hist_one(uint32_t *sh, unsigned long long key, uint32_t lane) {
-#pragma unroll
-	for (int c = 0; c < KB; ++c)
-		hist_add<KB>(sh, c, (uint32_t)(key >> (8 * c)) & 0xFFu, lane);
-}
-
-template <int ES, int KB>
 __global__ void __launch_bounds__(kHistThreads, 1)
-histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_t head,
-                 size_t n_vec, KeyDesc kd, unsigned long long *__restrict__ ghist,
-                 unsigned long long *__restrict__ gdescents) {
+histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_t head, size_t n_vec,
+                 KeyXform<std::conditional_t<(KB > 4), unsigned long long, uint32_t>> xf,
+                 unsigned long long *__restrict__ ghist, unsigned long long *__restrict__ gdescents) {
 	using R = typename Rec<ES>::type;
+	using KT = std::conditional_t<(KB > 4), unsigned long long, uint32_t>;
 	constexpr int VEC = 16 / ES;
 	extern __shared__ __align__(16) uint32_t sh[];
 	__shared__ uint32_t s_desc;
@@ -89,6 +130,11 @@ histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_
 	if (tid == 0)
 		s_desc = 0;
 	__syncthreads();
+	// lane-private copy: 32-bit copies -> word `lane` of each bin; 16-bit copies -> half (lane / 16)
+	// of word (lane % 16)
+	unsigned char *lane_base = reinterpret_cast<unsigned char *>(sh) +
+	                           (HistSmem<KB>::kPacked ? (lane & 15u) * 4u : lane * 4u);
+	const uint32_t inc = HistSmem<KB>::kPacked ? (1u << (lane & 16u)) : 1u;
 
 	uint32_t descents = 0;
 	const uint4 *vsrc = reinterpret_cast<const uint4 *>(src + head);
@@ -113,21 +159,21 @@ histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_
 		for (int u = 0; u < kHistUnroll; ++u) {
 			const size_t v = v0 + (size_t)u * stride;
 			const bool live = v < n_vec;
-			unsigned long long k[VEC];
+			KT k[VEC];
 			const R *e = reinterpret_cast<const R *>(&q[u]);
 #pragma unroll
 			for (int j = 0; j < VEC; ++j)
-				k[j] = derive_key(key_word<ES>(e[j], kd.word_sel), kd);
+				k[j] = derive_fast<ES, KT>(e[j], xf);
 			// successor of this vector's last record: next lane's first key, or a scalar load
-			unsigned long long nxt = __shfl_down_sync(0xFFFFFFFFu, k[0], 1);
+			KT nxt = __shfl_down_sync(0xFFFFFFFFu, k[0], 1);
 			const size_t next_idx = head + (v + 1) * VEC;
-			bool have_next = live && next_idx < n;
+			const bool have_next = live && next_idx < n;
 			if ((lane == 31 || v + 1 >= n_vec) && have_next)
-				nxt = derive_key(key_word<ES>(src[next_idx], kd.word_sel), kd);
+				nxt = derive_fast<ES, KT>(src[next_idx], xf);
 			if (live) {
 #pragma unroll
 				for (int j = 0; j < VEC; ++j)
-					hist_one<ES, KB>(sh, k[j], lane);
+					hist_one<KB, KT>(lane_base, k[j], inc);
 #pragma unroll
 				for (int j = 0; j + 1 < VEC; ++j)
 					descents += k[j] > k[j + 1];
@@ -151,10 +197,10 @@ histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_
 		const size_t extra = head + (n - tail0);
 		for (size_t t = tid; t < extra; t += kHistThreads) {
 			const size_t i = t < head ? t : tail0 + (t - head);
-			const unsigned long long k = derive_key(key_word<ES>(src[i], kd.word_sel), kd);
-			hist_one<ES, KB>(sh, k, lane);
+			const KT k = derive_fast<ES, KT>(src[i], xf);
+			hist_one<KB, KT>(lane_base, k, inc);
 			if (i + 1 < n)
-				descents += k > derive_key(key_word<ES>(src[i + 1], kd.word_sel), kd);
+				descents += k > derive_fast<ES, KT>(src[i + 1], xf);
 		}
 	}
 
@@ -240,8 +286,9 @@ cudaError_t launch_hist_t(const void *src, size_t n, const KeyDesc &kd, WsHead *
 	const size_t n_vec = (n - head) / VEC;
 	size_t want = (n_vec + (size_t)kHistThreads * kHistUnroll - 1) / ((size_t)kHistThreads * kHistUnroll);
 	int grid = (int)(want < (size_t)num_sms ? (want ? want : 1) : (size_t)num_sms);
+	using KT = std::conditional_t<(KB > 4), unsigned long long, uint32_t>;
 	kern<<<grid, kHistThreads, HistSmem<KB>::kBytes, st>>>(static_cast<const R *>(src), n, head, n_vec,
-	                                                      kd, ws->hist, &ws->descents);
+	                                                      make_xform<KT>(kd), ws->hist, &ws->descents);
 	count_launch();
 	return cudaGetLastError();
 }

@@ -318,3 +318,39 @@ def test_device_keygen_matches_host(rsx, torch, keygen):
             rsx.fill_keys(dst, seed=17, start=123456789, dist=dist, mask=0x00FFFFFFFFFFFF0F, orv=0x3)
             want = keygen.fill(17, 123456789, 10007, kb, dist, 0x00FFFFFFFFFFFF0F, 0x3)
             assert np.array_equal(dst.cpu().numpy().view(f"<u{kb}"), want), (dist, kb)
+
+
+# ---- the n >= 2^30 code path (64-bit look-back words and offsets) -----------------------------------------
+
+@pytest.mark.parametrize("tname", ["u32", "u64", "f32", "rec8_u32", "rec16_u64"])
+def test_wide_offset_kernels_at_small_n(rsx, torch, oracle, tname):
+    """radix_sort.hpp:111-113 switches to 64-bit counters at n >= 2^32; our look-back words and
+    offsets go 64-bit at n >= 2^30.  force_wide runs those kernels on oracle-sized inputs."""
+    t = TYPES[tname]
+    data = make_input(tname, 250007, 31, "and2")
+    try:
+        assert rsx.lib().rsx_set_option(b"force_wide", 1) == 0
+        out, rep, _ = gpu_sort(rsx, torch, tname, data)
+        ranks, _, _ = gpu_rank(rsx, torch, tname, data, np.uint64)
+    finally:
+        rsx.lib().rsx_set_option(b"force_wide", 0)
+    want, orep, _ = oracle.radix_sort(data, t.layout())
+    assert out.tobytes() == want.tobytes() and rep.result_in_aux == orep.result_in_aux
+    wr, _, _ = oracle.radix_sort_rank(data, t.layout(), np.uint64)
+    assert np.array_equal(ranks, wr)
+
+
+def test_more_than_2_pow_30_keys(rsx, torch):
+    """1.2 G u32 keys (> 2^30): sortedness + multiset checksum; masked to 3 live columns so the
+    result must land in aux."""
+    n = 1_200_000_000
+    src = torch.empty(n, dtype=torch.int32, device="cuda")
+    aux = torch.empty_like(src)
+    rsx.fill_keys(src, seed=9, mask=0x00FFFFFF)
+    kf = rsx.KeyFunc(rsx.KDF_UNSIGNED)
+    _, s0, x0 = rsx.verify(src, kf)
+    rep = rsx.RsxReport()
+    res = rsx.radix_sort(src, aux, None, kf, report=rep)
+    d1, s1, x1 = rsx.verify(res, kf)
+    assert d1 == 0 and (s1, x1) == (s0, x0)
+    assert rep.ncols == 3 and res.data_ptr() == aux.data_ptr()
