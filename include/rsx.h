@@ -106,6 +106,16 @@ int rsx_histogram(const void *src, size_t n, const rsx_layout *layout,
 int rsx_scatter_pass(const void *src, void *dst, const void *payload_src, void *payload_dst,
                      int payload_bytes, size_t n, const rsx_layout *layout, int col, void *stream);
 
+/* Fused partition + exchange for the multi-GPU sort (no reference equivalent):
+ * the same stable pass on column `col`, but bucket d is written to the byte address
+ * digit_dst[d] (256 HOST-side entries, copied by the call) instead of one contiguous dst --
+ * e.g. into another GPU's receive buffer mapped over NVLink, so that the all-to-all costs no
+ * extra HBM pass.  Bucket d's records land at digit_dst[d] + i * record_bytes in stable order.
+ * Returns after the pass has completed on this device; cross-device visibility additionally
+ * needs a barrier between the ranks. */
+int rsx_scatter_pass_to(const void *src, size_t n, const rsx_layout *layout, int col,
+                        const uint64_t *digit_dst, void *stream);
+
 /* ---- workspace ---------------------------------------------------------------------------
  * The reference allocates nothing (stack histograms).  The device path needs scratch for the
  * digit histograms, the pass table and the decoupled look-back state, and -- for rank sorts --

@@ -35,7 +35,8 @@ RSX_ERR_WORKSPACE, RSX_ERR_IDX_RANGE, RSX_ERR_MIXED_MEMORY = -4, -5, -6
 
 #: every symbol include/rsx.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "rsx_sort", "rsx_sort_rank", "rsx_histogram", "rsx_scatter_pass", "rsx_workspace_bytes",
+    "rsx_sort", "rsx_sort_rank", "rsx_histogram", "rsx_scatter_pass", "rsx_scatter_pass_to",
+    "rsx_workspace_bytes",
     "rsx_reserve", "rsx_release", "rsx_fill_keys", "rsx_verify", "rsx_strerror",
     "rsx_last_cuda_error", "rsx_version", "rsx_total_kernel_launches", "rsx_set_option",
     "rsx_get_profile",
@@ -86,6 +87,8 @@ def _lib() -> C.CDLL:
     L.rsx_histogram.argtypes = [vp, sz, LP, u64p, u64p, RP, vp]
     L.rsx_scatter_pass.restype = C.c_int
     L.rsx_scatter_pass.argtypes = [vp, vp, vp, vp, C.c_int, sz, LP, C.c_int, vp]
+    L.rsx_scatter_pass_to.restype = C.c_int
+    L.rsx_scatter_pass_to.argtypes = [vp, sz, LP, C.c_int, u64p, vp]
     L.rsx_workspace_bytes.restype = sz
     L.rsx_workspace_bytes.argtypes = [sz, LP, C.c_int]
     L.rsx_reserve.restype = C.c_int
@@ -267,6 +270,20 @@ def scatter_pass(src, dst, col: int, kf: Optional[KeyFunc] = None, payload_src=N
     if st != RSX_OK:
         raise RsxError(st, "rsx_scatter_pass")
     return dst
+
+
+def scatter_pass_to(src, col: int, digit_dst, kf: Optional[KeyFunc] = None):
+    """Fused partition + exchange: bucket d of the stable pass on `col` goes to byte address
+    digit_dst[d] (sequence of 256 ints; typically peer-GPU memory)."""
+    torch = _torch()
+    kf = kf or default_kdf(src.dtype)
+    L = kf.layout(src.element_size())
+    n = src.numel() * src.element_size() // L.record_bytes
+    table = (C.c_uint64 * 256)(*[int(x) for x in digit_dst])
+    with torch.cuda.device(src.device):
+        st = _lib().rsx_scatter_pass_to(src.data_ptr(), n, C.byref(L), col, table, _stream_ptr(src))
+    if st != RSX_OK:
+        raise RsxError(st, "rsx_scatter_pass_to")
 
 
 def fill_keys(dst, seed: int, start: int = 0, dist: str = "uniform", mask: int = (1 << 64) - 1,

@@ -411,7 +411,8 @@ PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes) {
 
 cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_bytes, int payload_bytes,
                            const KeyDesc &kd, int col, const WsHead *ws, bool forced, void *status,
-                           unsigned int *ticket, bool wide, int num_sms, cudaStream_t st) {
+                           unsigned int *ticket, bool wide, int num_sms, cudaStream_t st,
+                           const unsigned long long *digit_dst) {
 	ScatterParams sp;
 	sp.pb = pb;
 	sp.n = n;
@@ -427,6 +428,7 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
 	sp.ticket = ticket;
 	sp.pad_rec = pad_record(kd);
 	sp.dbg = nullptr;
+	sp.digit_dst = digit_dst;
 #ifdef RSX_PHASE_TIMING
 	{
 		static unsigned long long *d_dbg = nullptr;
@@ -835,6 +837,37 @@ int rsx_scatter_pass(const void *src, void *dst, const void *payload_src, void *
 	pb.pl_buf[1] = payload_dst;
 	if ((r = run_scatter(pb, P, col, ws, true, wsp + P.off_status, &ws->tickets[col], sms, st)))
 		return r;
+	CU(cudaStreamSynchronize(st));
+	return RSX_OK;
+}
+
+int rsx_scatter_pass_to(const void *src, size_t n, const rsx_layout *layout, int col,
+                        const uint64_t *digit_dst, void *stream) {
+	KeyDesc kd;
+	int r = check_layout(layout, &kd);
+	if (r)
+		return r;
+	if (!src || !digit_dst || n < 1 || col < 0 || col >= (int)kd.key_bytes)
+		return RSX_ERR_INVALID;
+	int dev;
+	if ((r = current_device(&dev)))
+		return r;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	Plan P;
+	make_plan(P, n, layout, kd, 0, 0);
+	Lease L;
+	if ((r = acquire(L, dev, P.total)))
+		return r;
+	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
+	const int sms = g_dev[dev].num_sms;
+	if ((r = enqueue_front(src, P, wsp, sms, st)))
+		return r;
+	CU(cudaMemcpyAsync(ws->digit_dst, digit_dst, sizeof(ws->digit_dst), cudaMemcpyHostToDevice, st));
+	PassBuffers pb{};
+	pb.rec_first = src;
+	CU(launch_scatter(pb, P.n, P.rb, 0, P.kd, col, ws, true, wsp + P.off_status, &ws->tickets[col], P.wide, sms, st,
+	                  ws->digit_dst));
 	CU(cudaStreamSynchronize(st));
 	return RSX_OK;
 }

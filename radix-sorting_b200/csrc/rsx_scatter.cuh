@@ -51,6 +51,10 @@ struct ScatterParams {
 	unsigned int *ticket;
 	ulonglong2 pad_rec;             // record whose derived key is all ones (tail padding)
 	unsigned long long *dbg;        // RSX_PHASE_TIMING builds only: per-phase cycle accumulators
+	// Fused partition + exchange (multi-GPU): when non-null, bucket d is not written to rec_buf but
+	// to the byte address digit_dst[d] (+ its position inside the bucket) -- typically a peer GPU's
+	// receive buffer mapped over NVLink.  256 entries in device memory.  Records only (no payload).
+	const unsigned long long *digit_dst;
 };
 
 #ifdef RSX_PHASE_TIMING
@@ -192,6 +196,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 	P *s_pl = reinterpret_cast<P *>(smem + SM::kOffSorted + SM::kRecBytes);
 	uint32_t *s_wh = reinterpret_cast<uint32_t *>(smem + SM::kOffWh);
 	OffT *s_gadj = reinterpret_cast<OffT *>(smem + SM::kOffAdj);
+	unsigned long long *s_gptr = reinterpret_cast<unsigned long long *>(smem + SM::kOffAdj); // fused mode view
 	OffT *s_lbsum = reinterpret_cast<OffT *>(smem + SM::kOffLb);
 	uint32_t *s_lbst = reinterpret_cast<uint32_t *>(smem + SM::kOffLb + (size_t)kBins * 8);
 	uint32_t *s_misc = reinterpret_cast<uint32_t *>(smem + SM::kOffMisc);
@@ -447,7 +452,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 				}
 				if (tile != 0)
 					st_status(&status[(size_t)tile * kBins + dgt], (OffT)(SB::kPfx | (excl + (OffT)tcount)));
-				s_gadj[dgt] = (OffT)p.offs[dgt] + excl - (OffT)tstart;
+				if (p.digit_dst != nullptr)
+					s_gptr[dgt] = p.digit_dst[dgt] + ((unsigned long long)excl - (unsigned long long)tstart) * ES;
+				else
+					s_gadj[dgt] = (OffT)p.offs[dgt] + excl - (OffT)tstart;
 			}
 		}
 		RSX_T(6);
@@ -460,7 +468,13 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		RSX_T(7);
 
 		// ---- 5. coalesced per-bucket stores ----
-		if (full) {
+		if (p.digit_dst != nullptr) { // straight into the owner's buffer (peer memory over NVLink)
+			for (uint32_t s = tid; s < valid; s += THREADS) {
+				const R r = s_rec[s];
+				R *dst = reinterpret_cast<R *>(s_gptr[digit_of<ES, FLOAT>(r, dd)]) + s;
+				*dst = r;
+			}
+		} else if (full) {
 #pragma unroll
 			for (int i = 0; i < ITEMS; ++i) {
 				const uint32_t s = tid + i * THREADS;

@@ -10,8 +10,12 @@ multi-device path; this is the MSD-then-LSD composition of its own primitives:
      ranks as contiguous ranges balancing the global counts
   4. one stable scatter pass (K3) on that column groups each rank's shard by bucket, hence by
      destination rank
-  5. all_to_all_single over NCCL/NVLink with the exact split sizes; the receiver concatenates
-     the chunks in source-rank order, which keeps the global order stable
+  5. exchange.  Fused form (default): step 4's kernel stores every bucket straight into its
+     owner's receive buffer -- peer memory mapped with torch symmetric memory, written over
+     NVLink -- so the all-to-all costs no extra HBM pass (rsx_scatter_pass_to).  Baseline form
+     (fused=False, or when symmetric memory is unavailable): all_to_all_single over NCCL with
+     the exact split sizes.  Either way a receive buffer holds the chunks in source-rank
+     order, which keeps the global order stable
   6. local LSD radix sort (K1-K3, device-side column skipping) of what was received
 
 The concatenation of the ranks' outputs in rank order is the globally sorted sequence, and it
@@ -63,6 +67,35 @@ class CudaEngine:
     def sort(self, src, aux, kf):
         return self.rsx.radix_sort(src, aux, None, kf)
 
+    # ---- fused partition + exchange over peer memory (NVLink) ----------------------------------
+    _symm = {}  # (dtype, device) -> (tensor, handle): symmetric receive buffer, grown on demand
+
+    def symmetric_recv(self, capacity, like, group):
+        """A receive buffer of >= capacity elements allocated symmetrically on every rank, with the
+        peers' addresses.  Returns (tensor, [base address per rank], handle) or None if symmetric
+        memory is not available here (the caller then uses the NCCL all-to-all)."""
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+        except Exception:
+            return None
+        key = (like.dtype, like.device.index)
+        cur = self._symm.get(key)
+        if cur is None or cur[0].numel() < capacity:
+            try:
+                t = symm_mem.empty(int(capacity * 1.02) + 1024, dtype=like.dtype, device=like.device)
+                h = symm_mem.rendezvous(t, group=group)
+                cur = (t, h)
+            except Exception as e:  # no fabric / P2P support
+                self._symm[key] = None
+                CudaEngine._symm_error = repr(e)
+                return None
+            self._symm[key] = cur
+        t, h = cur
+        return t, [int(p) for p in h.buffer_ptrs], h
+
+    def scatter_pass_to(self, src, col, digit_dst, kf):
+        self.rsx.scatter_pass_to(src, col, digit_dst, kf)
+
     def empty(self, n, like):
         return self.torch.empty(n, dtype=like.dtype, device=like.device)
 
@@ -104,7 +137,7 @@ class PartitionInfo:
     seconds: dict
 
 
-def partitioned_sort(keys, kf, group=None, engine=None, timers: bool = False):
+def partitioned_sort(keys, kf, group=None, engine=None, timers: bool = False, fused: bool = True):
     """Globally sorts the concatenation (in rank order) of every rank's `keys`.
     Returns (this rank's slice of the sorted sequence, PartitionInfo).  `keys` is clobbered."""
     import torch
@@ -150,20 +183,46 @@ def partitioned_sort(keys, kf, group=None, engine=None, timers: bool = False):
     recv = [int(per_rank[s, top, owner == rank].sum()) for s in range(world)]
     n_out = sum(recv)
 
-    # 4. group the shard by routing bucket (stable): destinations become contiguous ranges
     rec_elems = L.record_bytes // keys.element_size()
-    part = engine.empty(keys.numel(), keys)
-    engine.scatter_pass(keys, part, top, kf)
-    t = tick("partition_pass", t)
-
-    # 5. exchange
-    out_buf = engine.empty(max(n_out, 1) * rec_elems, keys)
-    dist.all_to_all_single(out_buf[: n_out * rec_elems], part, [r * rec_elems for r in recv],
-                           [s * rec_elems for s in send], group=group)
-    t = tick("all_to_all", t)
+    symm = None
+    if fused and hasattr(engine, "symmetric_recv"):
+        # every rank must take the same branch: capacity is the global maximum, known to all
+        cap = max(int(per_rank[:, top, owner == d].sum()) for d in range(world)) * rec_elems
+        symm = engine.symmetric_recv(max(cap, 1), keys, group)
+        ok = torch.tensor([1 if symm is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if not int(ok.item()):
+            symm = None
+    if symm is not None:
+        # 4+5 fused: the stable pass on the routing column stores every bucket straight into its
+        # owner's receive buffer (peer memory over NVLink).  Layout of a receive buffer: chunks in
+        # source-rank order, inside a chunk the owner's buckets in bucket order.
+        out_buf, bases, handle = symm
+        table = []
+        for b in range(256):
+            d = int(owner[b])
+            before_sources = int(per_rank[:rank, top, owner == d].sum())
+            before_buckets = int(per_rank[rank, top, :b][owner[:b] == d].sum())
+            table.append(bases[d] + (before_sources + before_buckets) * L.record_bytes)
+        handle.barrier()  # nobody is still sorting out of its receive buffer from the previous call
+        if n_local:
+            engine.scatter_pass_to(keys, top, table, kf)
+        torch.cuda.synchronize(dev)
+        handle.barrier()  # all remote stores have landed
+        t = tick("fused_partition_exchange", t)
+    else:
+        # 4. group the shard by routing bucket (stable): destinations become contiguous ranges
+        part = engine.empty(keys.numel(), keys)
+        engine.scatter_pass(keys, part, top, kf)
+        t = tick("partition_pass", t)
+        # 5. exchange
+        out_buf = engine.empty(max(n_out, 1) * rec_elems, keys)
+        dist.all_to_all_single(out_buf[: n_out * rec_elems], part, [r * rec_elems for r in recv],
+                               [s * rec_elems for s in send], group=group)
+        t = tick("all_to_all", t)
+        del part
 
     # 6. local LSD sort of the received records (chunks arrive in source-rank order: stable)
-    del part
     recv_view = out_buf[: n_out * rec_elems]
     if n_out > 1:
         aux = keys if keys.numel() >= recv_view.numel() else engine.empty(recv_view.numel(), keys)
@@ -171,6 +230,7 @@ def partitioned_sort(keys, kf, group=None, engine=None, timers: bool = False):
     else:
         res = recv_view
     t = tick("local_sort", t)
+    sec["exchange"] = "fused peer stores (NVLink)" if symm is not None else "NCCL all_to_all_single"
     info = PartitionInfo(top, live, send, recv, n_out, n_total, n_out / max(n_total / world, 1), sec)
     return res, info
 
@@ -200,7 +260,7 @@ def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        res, info = partitioned_sort(keys, kf, engine=engine)
+        res, info = partitioned_sort(keys, kf, engine=engine, fused=not getattr(args, "no_fused", False))
         e1.record()
         e1.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -241,7 +301,7 @@ def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world
     # one extra pass with host timers for the phase breakdown (not part of the timed steps)
     keys.copy_(pristine)
     dist.barrier()
-    _, info_t = partitioned_sort(keys, kf, engine=engine, timers=True)
+    _, info_t = partitioned_sort(keys, kf, engine=engine, timers=True, fused=not getattr(args, "no_fused", False))
     ms_per_step = sum(times) / len(times)
     n_total = n_per_gpu * world
     value = n_total / (ms_per_step * 1e-3) / 1e9
