@@ -107,14 +107,17 @@ int rsx_scatter_pass(const void *src, void *dst, const void *payload_src, void *
                      int payload_bytes, size_t n, const rsx_layout *layout, int col, void *stream);
 
 /* Fused partition + exchange for the multi-GPU sort (no reference equivalent):
- * the same stable pass on column `col`, but bucket d is written to the byte address
- * digit_dst[d] (256 HOST-side entries, copied by the call) instead of one contiguous dst --
- * e.g. into another GPU's receive buffer mapped over NVLink, so that the all-to-all costs no
- * extra HBM pass.  Bucket d's records land at digit_dst[d] + i * record_bytes in stable order.
- * Returns after the pass has completed on this device; cross-device visibility additionally
- * needs a barrier between the ranks. */
+ * the same stable pass on column `col`, but the output goes to `ndest` destinations instead of
+ * one dst: bucket d belongs to destination owner[d] (owner[] non-decreasing: contiguous bucket
+ * ranges) and every tile appends ONE contiguous run per destination at byte address
+ * dest_base[D] -- e.g. a peer GPU's receive buffer mapped over NVLink, so the all-to-all
+ * costs no extra HBM pass and every remote store run is KiBs long.  Inside a destination the
+ * records are in (tile, bucket, position) order: stable for equal keys, not grouped by bucket
+ * across tiles (the receiver's LSD sort does not need that).  owner / dest_base are HOST
+ * arrays (256 / ndest entries).  Returns after the pass has completed on this device;
+ * cross-device visibility additionally needs a barrier between the ranks. */
 int rsx_scatter_pass_to(const void *src, size_t n, const rsx_layout *layout, int col,
-                        const uint64_t *digit_dst, void *stream);
+                        const uint8_t *owner, const uint64_t *dest_base, int ndest, void *stream);
 
 /* ---- workspace ---------------------------------------------------------------------------
  * The reference allocates nothing (stack histograms).  The device path needs scratch for the

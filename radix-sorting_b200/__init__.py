@@ -88,7 +88,7 @@ def _lib() -> C.CDLL:
     L.rsx_scatter_pass.restype = C.c_int
     L.rsx_scatter_pass.argtypes = [vp, vp, vp, vp, C.c_int, sz, LP, C.c_int, vp]
     L.rsx_scatter_pass_to.restype = C.c_int
-    L.rsx_scatter_pass_to.argtypes = [vp, sz, LP, C.c_int, u64p, vp]
+    L.rsx_scatter_pass_to.argtypes = [vp, sz, LP, C.c_int, C.POINTER(C.c_uint8), u64p, C.c_int, vp]
     L.rsx_workspace_bytes.restype = sz
     L.rsx_workspace_bytes.argtypes = [sz, LP, C.c_int]
     L.rsx_reserve.restype = C.c_int
@@ -272,16 +272,19 @@ def scatter_pass(src, dst, col: int, kf: Optional[KeyFunc] = None, payload_src=N
     return dst
 
 
-def scatter_pass_to(src, col: int, digit_dst, kf: Optional[KeyFunc] = None):
-    """Fused partition + exchange: bucket d of the stable pass on `col` goes to byte address
-    digit_dst[d] (sequence of 256 ints; typically peer-GPU memory)."""
+def scatter_pass_to(src, col: int, owner, dest_base, kf: Optional[KeyFunc] = None):
+    """Fused partition + exchange: stable pass on `col` whose buckets go to destination
+    owner[bucket] (256 ints, non-decreasing); every tile appends one contiguous run per
+    destination at byte address dest_base[D] (typically peer-GPU memory)."""
     torch = _torch()
     kf = kf or default_kdf(src.dtype)
     L = kf.layout(src.element_size())
     n = src.numel() * src.element_size() // L.record_bytes
-    table = (C.c_uint64 * 256)(*[int(x) for x in digit_dst])
+    own = (C.c_uint8 * 256)(*[int(x) for x in owner])
+    base = (C.c_uint64 * len(dest_base))(*[int(x) for x in dest_base])
     with torch.cuda.device(src.device):
-        st = _lib().rsx_scatter_pass_to(src.data_ptr(), n, C.byref(L), col, table, _stream_ptr(src))
+        st = _lib().rsx_scatter_pass_to(src.data_ptr(), n, C.byref(L), col, own, base, len(dest_base),
+                                        _stream_ptr(src))
     if st != RSX_OK:
         raise RsxError(st, "rsx_scatter_pass_to")
 

@@ -412,7 +412,7 @@ PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes) {
 cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_bytes, int payload_bytes,
                            const KeyDesc &kd, int col, const WsHead *ws, bool forced, void *status,
                            unsigned int *ticket, bool wide, int num_sms, cudaStream_t st,
-                           const unsigned long long *digit_dst) {
+                           const unsigned long long *dest_base, const unsigned char *owner) {
 	ScatterParams sp;
 	sp.pb = pb;
 	sp.n = n;
@@ -428,7 +428,8 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
 	sp.ticket = ticket;
 	sp.pad_rec = pad_record(kd);
 	sp.dbg = nullptr;
-	sp.digit_dst = digit_dst;
+	sp.dest_base = dest_base;
+	sp.owner = owner;
 #ifdef RSX_PHASE_TIMING
 	{
 		static unsigned long long *d_dbg = nullptr;
@@ -842,13 +843,16 @@ int rsx_scatter_pass(const void *src, void *dst, const void *payload_src, void *
 }
 
 int rsx_scatter_pass_to(const void *src, size_t n, const rsx_layout *layout, int col,
-                        const uint64_t *digit_dst, void *stream) {
+                        const uint8_t *owner, const uint64_t *dest_base, int ndest, void *stream) {
 	KeyDesc kd;
 	int r = check_layout(layout, &kd);
 	if (r)
 		return r;
-	if (!src || !digit_dst || n < 1 || col < 0 || col >= (int)kd.key_bytes)
+	if (!src || !owner || !dest_base || n < 1 || col < 0 || col >= (int)kd.key_bytes || ndest < 1 || ndest > kBins)
 		return RSX_ERR_INVALID;
+	for (int b = 0; b < kBins; ++b) // contiguous ranges: owner is non-decreasing and < ndest
+		if (owner[b] >= ndest || (b && owner[b] < owner[b - 1]))
+			return RSX_ERR_INVALID;
 	int dev;
 	if ((r = current_device(&dev)))
 		return r;
@@ -863,11 +867,12 @@ int rsx_scatter_pass_to(const void *src, size_t n, const rsx_layout *layout, int
 	const int sms = g_dev[dev].num_sms;
 	if ((r = enqueue_front(src, P, wsp, sms, st)))
 		return r;
-	CU(cudaMemcpyAsync(ws->digit_dst, digit_dst, sizeof(ws->digit_dst), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ws->dest_base, dest_base, sizeof(uint64_t) * ndest, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ws->owner, owner, kBins, cudaMemcpyHostToDevice, st));
 	PassBuffers pb{};
 	pb.rec_first = src;
 	CU(launch_scatter(pb, P.n, P.rb, 0, P.kd, col, ws, true, wsp + P.off_status, &ws->tickets[col], P.wide, sms, st,
-	                  ws->digit_dst));
+	                  ws->dest_base, ws->owner));
 	CU(cudaStreamSynchronize(st));
 	return RSX_OK;
 }

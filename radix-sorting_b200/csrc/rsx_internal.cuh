@@ -46,7 +46,8 @@ struct WsHead {
 	// -- not zeroed below --
 	unsigned long long offs[kMaxCols * kBins]; // exclusive scan per column (radix_sort.hpp:72-80)
 	Ctl ctl;
-	unsigned long long digit_dst[kBins];       // fused partition + exchange: per-bucket destination address
+	unsigned long long dest_base[kBins];       // fused partition + exchange: per-destination base address
+	unsigned char owner[kBins];                // ... and the destination of every bucket
 };
 constexpr size_t kWsZeroBytes = offsetof(WsHead, offs);
 
@@ -84,7 +85,8 @@ cudaError_t launch_setup(const void *src, size_t n, uint32_t record_bytes, const
 cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_bytes, int payload_bytes,
                            const KeyDesc &kd, int col, const WsHead *ws_offsets /*offs + ctl*/,
                            bool forced, void *status, unsigned int *ticket, bool wide_offsets,
-                           int num_sms, cudaStream_t st, const unsigned long long *digit_dst = nullptr);
+                           int num_sms, cudaStream_t st, const unsigned long long *dest_base = nullptr,
+                           const unsigned char *owner = nullptr);
 
 PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes);
 

@@ -51,10 +51,13 @@ struct ScatterParams {
 	unsigned int *ticket;
 	ulonglong2 pad_rec;             // record whose derived key is all ones (tail padding)
 	unsigned long long *dbg;        // RSX_PHASE_TIMING builds only: per-phase cycle accumulators
-	// Fused partition + exchange (multi-GPU): when non-null, bucket d is not written to rec_buf but
-	// to the byte address digit_dst[d] (+ its position inside the bucket) -- typically a peer GPU's
-	// receive buffer mapped over NVLink.  256 entries in device memory.  Records only (no payload).
-	const unsigned long long *digit_dst;
+	// Fused partition + exchange (multi-GPU): when dest_base is non-null, bucket d belongs to
+	// destination owner[d] (contiguous bucket ranges) and every tile appends ONE contiguous run
+	// per destination at dest_base[D] -- typically a peer GPU's receive buffer mapped over NVLink.
+	// Inside a destination the order is (tile, bucket, position): stable, not grouped by bucket
+	// across tiles (the receiver's LSD sort does not need that).  Records only (no payload).
+	const unsigned long long *dest_base; // device memory, one byte address per destination
+	const unsigned char *owner;          // device memory, 256 entries
 };
 
 #ifdef RSX_PHASE_TIMING
@@ -171,7 +174,8 @@ template <int ES, int PL, class Cfg> struct ScatterSmem {
 	static constexpr size_t kOffWh = kOffSorted + kRecBytes + kPlBytes;
 	static constexpr size_t kOffAdj = kOffWh + kWhBytes;
 	static constexpr size_t kOffLb = kOffAdj + kAdjBytes; // look-back partner partials: 256 x (8 + 4) bytes
-	static constexpr size_t kOffMisc = kOffLb + (size_t)kBins * 12;
+	static constexpr size_t kOffDst = kOffLb + (size_t)kBins * 12; // fused mode: per-destination offsets
+	static constexpr size_t kOffMisc = kOffDst + (size_t)kBins * 12;
 	static constexpr size_t kBytes = kOffMisc + 64;
 };
 
@@ -197,6 +201,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 	uint32_t *s_wh = reinterpret_cast<uint32_t *>(smem + SM::kOffWh);
 	OffT *s_gadj = reinterpret_cast<OffT *>(smem + SM::kOffAdj);
 	unsigned long long *s_gptr = reinterpret_cast<unsigned long long *>(smem + SM::kOffAdj); // fused mode view
+	unsigned long long *s_dexcl = reinterpret_cast<unsigned long long *>(smem + SM::kOffDst); // fused mode
+	uint32_t *s_dstart = reinterpret_cast<uint32_t *>(smem + SM::kOffDst + (size_t)kBins * 8);
 	OffT *s_lbsum = reinterpret_cast<OffT *>(smem + SM::kOffLb);
 	uint32_t *s_lbst = reinterpret_cast<uint32_t *>(smem + SM::kOffLb + (size_t)kBins * 8);
 	uint32_t *s_misc = reinterpret_cast<uint32_t *>(smem + SM::kOffMisc);
@@ -231,6 +237,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 	OffT *status = static_cast<OffT *>(p.status);
 	const R pad = make_pad<ES>(p.pad_rec);
 	const uint32_t full_tiles = (uint32_t)(p.n / TILE); // tiles [0, full_tiles) are complete
+	const uint32_t my_owner = (p.dest_base != nullptr && tid < kBins) ? p.owner[tid] : 0u;
 
 	auto prefetch = [&](uint32_t t) { // one thread
 		const size_t base = (size_t)t * TILE;
@@ -275,6 +282,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 			uint4 *z = reinterpret_cast<uint4 *>(wh);
 			z[lane] = make_uint4(0, 0, 0, 0);
 			z[lane + 32] = make_uint4(0, 0, 0, 0);
+			if (p.dest_base != nullptr && tid < kBins)
+				s_dexcl[tid] = 0;
 		}
 		if (staged) {
 			mbar_wait(s_bar, phase);
@@ -452,10 +461,18 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 				}
 				if (tile != 0)
 					st_status(&status[(size_t)tile * kBins + dgt], (OffT)(SB::kPfx | (excl + (OffT)tcount)));
-				if (p.digit_dst != nullptr)
-					s_gptr[dgt] = p.digit_dst[dgt] + ((unsigned long long)excl - (unsigned long long)tstart) * ES;
-				else
+				if (p.dest_base != nullptr) {
+					// per-destination running offset = sum of its buckets' exclusive prefixes; the
+					// destination's records are one contiguous range of the tile-sorted buffer
+					const uint32_t D = my_owner;
+					atomicAdd(&s_dexcl[D], (unsigned long long)excl);
+					if (dgt == 0 || p.owner[dgt - 1] != D)
+						s_dstart[D] = tstart;
+					asm volatile("bar.sync 1, 256;" ::: "memory");
+					s_gptr[dgt] = p.dest_base[D] + (s_dexcl[D] - (unsigned long long)s_dstart[D]) * ES;
+				} else {
 					s_gadj[dgt] = (OffT)p.offs[dgt] + excl - (OffT)tstart;
+				}
 			}
 		}
 		RSX_T(6);
@@ -468,7 +485,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		RSX_T(7);
 
 		// ---- 5. coalesced per-bucket stores ----
-		if (p.digit_dst != nullptr) { // straight into the owner's buffer (peer memory over NVLink)
+		if (p.dest_base != nullptr) { // straight into the owner's buffer (peer memory over NVLink)
 			for (uint32_t s = tid; s < valid; s += THREADS) {
 				const R r = s_rec[s];
 				R *dst = reinterpret_cast<R *>(s_gptr[digit_of<ES, FLOAT>(r, dd)]) + s;

@@ -69,6 +69,7 @@ class CudaEngine:
 
     # ---- fused partition + exchange over peer memory (NVLink) ----------------------------------
     _symm = {}  # (dtype, device) -> (tensor, handle): symmetric receive buffer, grown on demand
+    symm_error = None
 
     def symmetric_recv(self, capacity, like, group):
         """A receive buffer of >= capacity elements allocated symmetrically on every rank, with the
@@ -78,23 +79,26 @@ class CudaEngine:
             import torch.distributed._symmetric_memory as symm_mem
         except Exception:
             return None
+        import torch.distributed as dist
         key = (like.dtype, like.device.index)
+        if key in self._symm and self._symm[key] is None:
+            return None  # failed before: do not retry on every call
         cur = self._symm.get(key)
         if cur is None or cur[0].numel() < capacity:
             try:
                 t = symm_mem.empty(int(capacity * 1.02) + 1024, dtype=like.dtype, device=like.device)
-                h = symm_mem.rendezvous(t, group=group)
+                h = symm_mem.rendezvous(t, group=group if group is not None else dist.group.WORLD)
                 cur = (t, h)
             except Exception as e:  # no fabric / P2P support
                 self._symm[key] = None
-                CudaEngine._symm_error = repr(e)
+                CudaEngine.symm_error = repr(e)
                 return None
             self._symm[key] = cur
         t, h = cur
         return t, [int(p) for p in h.buffer_ptrs], h
 
-    def scatter_pass_to(self, src, col, digit_dst, kf):
-        self.rsx.scatter_pass_to(src, col, digit_dst, kf)
+    def scatter_pass_to(self, src, col, owner, dest_base, kf):
+        self.rsx.scatter_pass_to(src, col, owner, dest_base, kf)
 
     def empty(self, n, like):
         return self.torch.empty(n, dtype=like.dtype, device=like.device)
@@ -194,19 +198,14 @@ def partitioned_sort(keys, kf, group=None, engine=None, timers: bool = False, fu
         if not int(ok.item()):
             symm = None
     if symm is not None:
-        # 4+5 fused: the stable pass on the routing column stores every bucket straight into its
-        # owner's receive buffer (peer memory over NVLink).  Layout of a receive buffer: chunks in
-        # source-rank order, inside a chunk the owner's buckets in bucket order.
+        # 4+5 fused: the stable pass on the routing column stores every destination's records
+        # straight into that rank's receive buffer (peer memory over NVLink), one contiguous run
+        # per (tile, destination).  Layout of a receive buffer: chunks in source-rank order.
         out_buf, bases, handle = symm
-        table = []
-        for b in range(256):
-            d = int(owner[b])
-            before_sources = int(per_rank[:rank, top, owner == d].sum())
-            before_buckets = int(per_rank[rank, top, :b][owner[:b] == d].sum())
-            table.append(bases[d] + (before_sources + before_buckets) * L.record_bytes)
+        dest_base = [bases[d] + int(per_rank[:rank, top, owner == d].sum()) * L.record_bytes for d in range(world)]
         handle.barrier()  # nobody is still sorting out of its receive buffer from the previous call
         if n_local:
-            engine.scatter_pass_to(keys, top, table, kf)
+            engine.scatter_pass_to(keys, top, owner, dest_base, kf)
         torch.cuda.synchronize(dev)
         handle.barrier()  # all remote stores have landed
         t = tick("fused_partition_exchange", t)
@@ -316,7 +315,7 @@ def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world
                    "imbalance_max_over_mean": max(n_outs) / (n_total / world), "verified": verified,
                    "timing": "CUDA events per rank around partitioned_sort, all_reduce MAX over ranks, mean of steps",
                    "l2": "inputs larger than L2, restored before every step",
-                   "phase_seconds_rank0": info_t.seconds},
+                   "phase_seconds_rank0": info_t.seconds, "symm_error": CudaEngine.symm_error},
         "roofline": {"bound": "hbm", "kernel": "whole partitioned sort, per GPU", "achieved": moved / (ms_per_step * 1e-3) / 1e9,
                      "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
                      "note": "per-GPU algorithmic HBM bytes (histogram + partition pass + local LSD) over the step time; "

@@ -354,3 +354,36 @@ def test_more_than_2_pow_30_keys(rsx, torch):
     d1, s1, x1 = rsx.verify(res, kf)
     assert d1 == 0 and (s1, x1) == (s0, x0)
     assert rep.ncols == 3 and res.data_ptr() == aux.data_ptr()
+
+
+# ---- fused partition + exchange pass (multi-GPU building block), on one device ----------------------------
+
+@pytest.mark.parametrize("tname,col", [("u32", 3), ("u64", 7), ("rec8_u32", 3), ("f32", 3)])
+def test_scatter_pass_to_destinations(rsx, torch, oracle, tname, col):
+    """rsx_scatter_pass_to with three local 'destinations': each receives exactly the records whose
+    routing bucket it owns, in an order that a stable local sort turns into the oracle's order."""
+    t = TYPES[tname]
+    n = 300007
+    data = make_input(tname, n, 21, "and2" if tname != "f32" else "uniform")
+    src = to_dev(torch, data)
+    L = t.layout()
+    u = (data["key"] if data.dtype.names else data).view(f"<u{t.key_bytes}").astype(np.uint64)
+    top = np.uint64(1 << (8 * t.key_bytes - 1))
+    m = np.uint64((1 << (8 * t.key_bytes)) - 1)
+    if t.kdf_kind == 2:
+        u = np.where(u & top, u ^ m, u ^ top)
+    digits = ((u >> np.uint64(8 * col)) & np.uint64(0xFF)).astype(np.int64)
+    owner = np.zeros(256, dtype=np.int64)
+    owner[40:200] = 1
+    owner[200:] = 2
+    counts = [int((owner[digits] == d).sum()) for d in range(3)]
+    bufs = [torch.full((max(c, 1) * t.record_bytes,), 0xAB, dtype=torch.uint8, device="cuda") for c in counts]
+    rsx.scatter_pass_to(src, col, owner, [b.data_ptr() for b in bufs], kf_for(rsx, tname))
+    torch.cuda.synchronize()
+    for d in range(3):
+        sub = data[owner[digits] == d]
+        got = bufs[d][: counts[d] * t.record_bytes]
+        aux = torch.zeros_like(got)
+        res = rsx.radix_sort(got, aux, None, kf_for(rsx, tname))
+        want, _, _ = oracle.radix_sort(sub, L)
+        assert res.cpu().numpy().tobytes() == want.tobytes(), f"destination {d}"
