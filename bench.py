@@ -230,7 +230,7 @@ def main():
         if not explicit_workload:
             import copy
             a2 = copy.copy(args)
-            a2.workload, a2.steps, a2.warmup = "2B-u64-uniform", min(args.steps, 3), 3
+            a2.workload, a2.steps, a2.warmup, a2.no_e2e = "2B-u64-uniform", min(args.steps, 3), 3, True
             t2, n2, d2, m2, o2, _ = WORKLOADS[a2.workload]
             torch.cuda.empty_cache()
             r2 = dsort.bench_partitioned(a2, rsx, t2, n2, d2, m2, o2, rank, world, dev)
