@@ -304,26 +304,36 @@ def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world
     # e2e: every rank's shard starts and ends in pinned HOST memory (H2D + global sort + D2H timed)
     e2e = None
     if not getattr(args, "no_e2e", False):
-        h_in = torch.empty(n_per_gpu, dtype=tdt, pin_memory=True)
-        h_in.copy_(pristine)
-        h_out = torch.empty(int(n_per_gpu * 1.25) + 1024, dtype=tdt, pin_memory=True)
-        e2e_t = []
-        for it in range(3):
-            dist.barrier()
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            keys.copy_(h_in, non_blocking=True)
-            r_e, info_e = partitioned_sort(keys, kf, engine=engine, fused=not getattr(args, "no_fused", False))
-            h_out[: info_e.n_out].copy_(r_e.view(-1)[: info_e.n_out], non_blocking=True)
-            torch.cuda.synchronize(dev)
-            dt = torch.tensor([time.perf_counter() - t0], device=dev)
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            if it:
-                e2e_t.append(float(dt.item()))
-        e2e_s = sum(e2e_t) / len(e2e_t)
-        e2e = {"value": n_per_gpu * world / e2e_s / 1e9, "unit": "Gkeys/s", "h2d_bytes_per_step": n_per_gpu * kb * world,
-               "d2h_bytes_per_step": n_per_gpu * kb * world, "ms_per_step": e2e_s * 1e3, "steps": len(e2e_t),
-               "note": "per rank: pinned host shard -> device, partitioned global sort, sorted shard -> pinned host; wall clock, max over ranks"}
+        h_in = h_out = None
+        try:
+            h_in = torch.empty(n_per_gpu, dtype=tdt, pin_memory=True)
+            h_out = torch.empty(int(n_per_gpu * 1.25) + 1024, dtype=tdt, pin_memory=True)
+            ok = 1
+        except Exception:  # not enough pinnable host memory for N shards on this box
+            ok = 0
+        okt = torch.tensor([ok], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)  # all ranks take the same branch
+        if int(okt.item()):
+            h_in.copy_(pristine)
+            e2e_t = []
+            for it in range(3):
+                dist.barrier()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                keys.copy_(h_in, non_blocking=True)
+                r_e, info_e = partitioned_sort(keys, kf, engine=engine, fused=not getattr(args, "no_fused", False))
+                h_out[: info_e.n_out].copy_(r_e.view(-1)[: info_e.n_out], non_blocking=True)
+                torch.cuda.synchronize(dev)
+                dt = torch.tensor([time.perf_counter() - t0], device=dev)
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                if it:
+                    e2e_t.append(float(dt.item()))
+            e2e_s = sum(e2e_t) / len(e2e_t)
+            e2e = {"value": n_per_gpu * world / e2e_s / 1e9, "unit": "Gkeys/s", "h2d_bytes_per_step": n_per_gpu * kb * world,
+                   "d2h_bytes_per_step": n_per_gpu * kb * world, "ms_per_step": e2e_s * 1e3, "steps": len(e2e_t),
+                   "note": "per rank: pinned host shard -> device, partitioned global sort, sorted shard -> pinned host; wall clock, max over ranks"}
+        else:
+            e2e = {"value": None, "unit": "Gkeys/s", "error": "could not pin host memory for every rank's shard"}
         del h_in, h_out
     ms_per_step = sum(times) / len(times)
     n_total = n_per_gpu * world
