@@ -145,7 +145,8 @@ template <int T, int I, int MB, int LBK, bool ST> struct CfgT {
 // shared-memory/LSU data pipe, so the largest tile that still leaves two CTAs per SM (4-byte
 // records) or one fat CTA (wider records) wins.
 template <int ES, int PL, int V> struct ScatterCfgV
-	: CfgT<512, ((ES + PL <= 4) ? 20 : (ES + PL <= 8) ? 16 : (ES + PL <= 16) ? 8 : 4), ((ES + PL <= 4) ? 2 : 1), 16, true> {};
+	: CfgT<((ES + PL > 4 && ES + PL <= 8) ? 1024 : 512),
+	       ((ES + PL <= 4) ? 20 : (ES + PL <= 8) ? 10 : (ES + PL <= 16) ? 8 : 4), ((ES + PL <= 4) ? 2 : 1), 16, true> {};
 constexpr int kNumVariants = 6;
 // tuning variants exist for plain 4- and 8-byte keys only
 template <> struct ScatterCfgV<4, 0, 1> : CfgT<512, 16, 2, 16, true> {};
@@ -157,7 +158,7 @@ template <> struct ScatterCfgV<8, 0, 1> : CfgT<512, 8, 2, 16, true> {};
 template <> struct ScatterCfgV<8, 0, 2> : CfgT<512, 10, 2, 16, true> {};
 template <> struct ScatterCfgV<8, 0, 3> : CfgT<1024, 8, 1, 16, true> {};
 template <> struct ScatterCfgV<8, 0, 4> : CfgT<512, 12, 1, 16, true> {};
-template <> struct ScatterCfgV<8, 0, 5> : CfgT<1024, 10, 1, 16, true> {};
+template <> struct ScatterCfgV<8, 0, 5> : CfgT<512, 16, 1, 16, true> {};
 template <int ES, int PL> using ScatterCfg = ScatterCfgV<ES, PL, 0>;
 int scatter_variant();
 
@@ -176,7 +177,7 @@ template <int ES, int PL, class Cfg> struct ScatterSmem {
 	static constexpr size_t kOffLb = kOffAdj + kAdjBytes; // look-back partner partials: 256 x (8 + 4) bytes
 	static constexpr size_t kOffDst = kOffLb + (size_t)kBins * 12; // fused mode: per-destination offsets
 	static constexpr size_t kOffMisc = kOffDst + (size_t)kBins * 12;
-	static constexpr size_t kBytes = kOffMisc + 64;
+	static constexpr size_t kBytes = kOffMisc + 96;
 };
 
 enum { RANK_TICKET = 0, RANK_BALLOT = 1 };
@@ -206,8 +207,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 	OffT *s_lbsum = reinterpret_cast<OffT *>(smem + SM::kOffLb);
 	uint32_t *s_lbst = reinterpret_cast<uint32_t *>(smem + SM::kOffLb + (size_t)kBins * 8);
 	uint32_t *s_misc = reinterpret_cast<uint32_t *>(smem + SM::kOffMisc);
-	unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem + SM::kOffMisc + 48);
-	// s_misc[0] = next tile ticket, s_misc[1..8] = warp totals of the digit scan
+	unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem + SM::kOffMisc + 80);
+	// s_misc[0] = next tile ticket, [1..8] = warp totals of the digit scan, [9] = hot digit,
+	// [10..17] = per-warp maxima of (count << 8 | digit)
 
 	// ---- pass table (device-side column skipping, radix_sort.hpp:60-70) ----
 	uint32_t ord = 0;
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		mbar_init(s_bar, 1);
 		const uint32_t t = atomicAdd(p.ticket, 1u);
 		s_misc[0] = t;
+		s_misc[9] = 0; // first tile: digit 0 as the hot-digit guess
 		if (can_stage && t < full_tiles)
 			prefetch(t);
 	}
@@ -306,9 +309,24 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		// ---- 2. rank inside the warp (stable: items ascending, lanes ascending) ----
 		uint32_t rank[ITEMS];
 		if constexpr (RANK == RANK_TICKET) {
+			// The tile's most frequent digit of the previous tile ("hot") is ranked in registers:
+			// one vote per item instead of up to 32 same-address atomics when a digit dominates
+			// (low-entropy columns); for uniform digits it only removes a few lanes from the atomic.
+			const uint32_t hot = s_misc[9];
+			uint32_t hotcnt = 0;
 #pragma unroll
-			for (int i = 0; i < ITEMS; ++i)
-				rank[i] = atomicAdd(&wh[digit_of<ES, FLOAT>(s_stage[t0 + i * 32], dd)], 1u);
+			for (int i = 0; i < ITEMS; ++i) {
+				const uint32_t d = digit_of<ES, FLOAT>(s_stage[t0 + i * 32], dd);
+				const bool is_hot = d == hot;
+				const uint32_t m = __ballot_sync(FULL, is_hot);
+				if (is_hot)
+					rank[i] = hotcnt + __popc(m & lt);
+				else
+					rank[i] = atomicAdd(&wh[d], 1u);
+				hotcnt += __popc(m);
+			}
+			if (lane == 0)
+				wh[hot] = hotcnt; // no atomic touched this counter
 		} else {
 #pragma unroll
 			for (int i = 0; i < ITEMS; ++i) {
@@ -353,13 +371,20 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 				if (lane >= o)
 					x += y;
 			}
-			if (lane == 31)
+			const uint32_t wmax = __reduce_max_sync(FULL, (tcount << 8) | tid); // hot digit for the next tile
+			if (lane == 31) {
 				s_misc[1 + warp] = x;
+				s_misc[10 + warp] = wmax;
+			}
 			asm volatile("bar.sync 1, 256;" ::: "memory");
-			uint32_t wbase = 0;
+			uint32_t wbase = 0, hmax = 0;
 #pragma unroll
-			for (int w = 0; w < 8; ++w)
+			for (int w = 0; w < 8; ++w) {
 				wbase += (w < (int)warp) ? s_misc[1 + w] : 0u;
+				hmax = max(hmax, s_misc[10 + w]);
+			}
+			if (tid == 0)
+				s_misc[9] = hmax & 0xFFu;
 			tstart = wbase + x - tcount;
 			uint32_t run = tstart;
 #pragma unroll

@@ -9,7 +9,7 @@ try:
 except Exception as e: print("ERR", f, e, open(f.replace(".json",".err")).read()[-800:])
 PY
 }
-for wl in 1B-u32-uniform 1B-u64-uniform; do
+for wl in $WORKLOADS; do
 for v in $VARIANTS; do
 timeout 300 python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu --workload $wl --variant $v > gpurun_out/bench_${wl}_v$v.json 2> gpurun_out/bench_${wl}_v$v.err; show gpurun_out/bench_${wl}_v$v.json
 done; done
