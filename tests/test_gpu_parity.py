@@ -387,3 +387,21 @@ def test_scatter_pass_to_destinations(rsx, torch, oracle, tname, col):
         res = rsx.radix_sort(got, aux, None, kf_for(rsx, tname))
         want, _, _ = oracle.radix_sort(sub, L)
         assert res.cpu().numpy().tobytes() == want.tobytes(), f"destination {d}"
+
+
+def test_more_than_2_pow_32_records(rsx, torch):
+    """n >= 2^32 -- the reference's 64-bit counter tier (radix_sort.hpp:111-113): 4.3 G one-byte
+    keys, one live column, result in aux; checked by descents + multiset checksum."""
+    n = (1 << 32) + 12345
+    src = torch.empty(n, dtype=torch.uint8, device="cuda")
+    aux = torch.empty_like(src)
+    rsx.fill_keys(src, seed=3)
+    kf = rsx.KeyFunc(rsx.KDF_UNSIGNED)
+    _, s0, x0 = rsx.verify(src, kf)
+    rep = rsx.RsxReport()
+    res = rsx.radix_sort(src, aux, None, kf, report=rep)
+    d1, s1, x1 = rsx.verify(res, kf)
+    assert d1 == 0 and (s1, x1) == (s0, x0)
+    assert rep.ncols == 1 and res.data_ptr() == aux.data_ptr()
+    hist, descents, _ = rsx.histogram(res, kf)
+    assert int(hist.sum()) == n and descents == 0
