@@ -40,6 +40,8 @@ WORKLOADS = {
     "500M-f32": ("f32", 500_000_000, "uniform", _M64, 0, 4),               # BASELINE configs[2]
     "500M-i64": ("i64", 500_000_000, "uniform", _M64, 0, 8),
     "2B-u64-uniform": ("u64", 2_000_000_000, "uniform", _M64, 0, 8),       # per-GPU shard of configs[4]
+    "2B-u64-zipf": ("u64", 2_000_000_000, "zipf", _M64, 0, 4),             # configs[4], skewed: P(v) ~ 1/v, v < 2^32
+    "1B-u32-zipf": ("u32", 1_000_000_000, "zipf", _M64, 0, 4),
 }
 CPU_SAMPLE_KEYS = {4: 256_000_000, 8: 96_000_000}  # bounded CPU sample, ~10-30 s of single-core work
 

@@ -119,6 +119,17 @@ int rsx_scatter_pass(const void *src, void *dst, const void *payload_src, void *
 int rsx_scatter_pass_to(const void *src, size_t n, const rsx_layout *layout, int col,
                         const uint8_t *owner, const uint64_t *dest_base, int ndest, void *stream);
 
+/* Key-range routing for skewed multi-GPU inputs (sample-sort style): `splitters` are nsplit
+ * (<= 15) ascending DERIVED keys; a record's destination is the number of splitters <= its
+ * derived key (0 .. nsplit).  rsx_split_counts counts the records per destination (HOST array of
+ * nsplit + 1 entries); rsx_split_pass_to is the stable fused partition pass with that routing:
+ * every tile appends one contiguous run per destination at byte address dest_base[D] (HOST array
+ * of nsplit + 1 addresses: local or peer memory), records in input order inside a destination. */
+int rsx_split_counts(const void *src, size_t n, const rsx_layout *layout, const uint64_t *splitters, int nsplit,
+                     uint64_t *counts_out, void *stream);
+int rsx_split_pass_to(const void *src, size_t n, const rsx_layout *layout, const uint64_t *splitters, int nsplit,
+                      const uint64_t *dest_base, void *stream);
+
 /* ---- workspace ---------------------------------------------------------------------------
  * The reference allocates nothing (stack histograms).  The device path needs scratch for the
  * digit histograms, the pass table and the decoupled look-back state, and -- for rank sorts --

@@ -36,6 +36,7 @@ RSX_ERR_WORKSPACE, RSX_ERR_IDX_RANGE, RSX_ERR_MIXED_MEMORY = -4, -5, -6
 #: every symbol include/rsx.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "rsx_sort", "rsx_sort_rank", "rsx_histogram", "rsx_scatter_pass", "rsx_scatter_pass_to",
+    "rsx_split_counts", "rsx_split_pass_to",
     "rsx_workspace_bytes",
     "rsx_reserve", "rsx_release", "rsx_fill_keys", "rsx_verify", "rsx_strerror",
     "rsx_last_cuda_error", "rsx_version", "rsx_total_kernel_launches", "rsx_set_option",
@@ -89,6 +90,10 @@ def _lib() -> C.CDLL:
     L.rsx_scatter_pass.argtypes = [vp, vp, vp, vp, C.c_int, sz, LP, C.c_int, vp]
     L.rsx_scatter_pass_to.restype = C.c_int
     L.rsx_scatter_pass_to.argtypes = [vp, sz, LP, C.c_int, C.POINTER(C.c_uint8), u64p, C.c_int, vp]
+    L.rsx_split_counts.restype = C.c_int
+    L.rsx_split_counts.argtypes = [vp, sz, LP, u64p, C.c_int, u64p, vp]
+    L.rsx_split_pass_to.restype = C.c_int
+    L.rsx_split_pass_to.argtypes = [vp, sz, LP, u64p, C.c_int, u64p, vp]
     L.rsx_workspace_bytes.restype = sz
     L.rsx_workspace_bytes.argtypes = [sz, LP, C.c_int]
     L.rsx_reserve.restype = C.c_int
@@ -287,6 +292,36 @@ def scatter_pass_to(src, col: int, owner, dest_base, kf: Optional[KeyFunc] = Non
                                         _stream_ptr(src))
     if st != RSX_OK:
         raise RsxError(st, "rsx_scatter_pass_to")
+
+
+def split_counts(src, splitters, kf: Optional[KeyFunc] = None):
+    """Records per key range: range index = number of (ascending, derived-key) splitters <= key."""
+    torch = _torch()
+    kf = kf or default_kdf(src.dtype)
+    L = kf.layout(src.element_size())
+    n = src.numel() * src.element_size() // L.record_bytes
+    sp = (C.c_uint64 * len(splitters))(*[int(x) for x in splitters])
+    out = (C.c_uint64 * (len(splitters) + 1))()
+    with torch.cuda.device(src.device):
+        st = _lib().rsx_split_counts(src.data_ptr(), n, C.byref(L), sp, len(splitters), out, _stream_ptr(src))
+    if st != RSX_OK:
+        raise RsxError(st, "rsx_split_counts")
+    return [int(x) for x in out]
+
+
+def split_pass_to(src, splitters, dest_base, kf: Optional[KeyFunc] = None):
+    """Stable partition by key range; range D is appended at byte address dest_base[D]."""
+    torch = _torch()
+    kf = kf or default_kdf(src.dtype)
+    L = kf.layout(src.element_size())
+    n = src.numel() * src.element_size() // L.record_bytes
+    sp = (C.c_uint64 * len(splitters))(*[int(x) for x in splitters])
+    base = (C.c_uint64 * len(dest_base))(*[int(x) for x in dest_base])
+    assert len(dest_base) == len(splitters) + 1
+    with torch.cuda.device(src.device):
+        st = _lib().rsx_split_pass_to(src.data_ptr(), n, C.byref(L), sp, len(splitters), base, _stream_ptr(src))
+    if st != RSX_OK:
+        raise RsxError(st, "rsx_split_pass_to")
 
 
 def fill_keys(dst, seed: int, start: int = 0, dist: str = "uniform", mask: int = (1 << 64) - 1,

@@ -412,7 +412,8 @@ PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes) {
 cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_bytes, int payload_bytes,
                            const KeyDesc &kd, int col, const WsHead *ws, bool forced, void *status,
                            unsigned int *ticket, bool wide, int num_sms, cudaStream_t st,
-                           const unsigned long long *dest_base, const unsigned char *owner) {
+                           const unsigned long long *dest_base, const unsigned char *owner,
+                           const unsigned long long *splitters, int nsplit) {
 	ScatterParams sp;
 	sp.pb = pb;
 	sp.n = n;
@@ -430,6 +431,10 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
 	sp.dbg = nullptr;
 	sp.dest_base = dest_base;
 	sp.owner = owner;
+	sp.kd = kd;
+	sp.nsplit = (uint32_t)nsplit;
+	for (int j = 0; j < kMaxSplit; ++j)
+		sp.split[j] = (splitters && j < nsplit) ? splitters[j] : ~0ULL;
 #ifdef RSX_PHASE_TIMING
 	{
 		static unsigned long long *d_dbg = nullptr;
@@ -873,6 +878,84 @@ int rsx_scatter_pass_to(const void *src, size_t n, const rsx_layout *layout, int
 	pb.rec_first = src;
 	CU(launch_scatter(pb, P.n, P.rb, 0, P.kd, col, ws, true, wsp + P.off_status, &ws->tickets[col], P.wide, sms, st,
 	                  ws->dest_base, ws->owner));
+	CU(cudaStreamSynchronize(st));
+	return RSX_OK;
+}
+
+// Key-range routing (sample-sort style splitters) for skewed multi-GPU inputs.
+static int check_splitters(const uint64_t *splitters, int nsplit) {
+	if (!splitters || nsplit < 1 || nsplit > kMaxSplit)
+		return RSX_ERR_INVALID;
+	for (int j = 1; j < nsplit; ++j)
+		if (splitters[j] < splitters[j - 1])
+			return RSX_ERR_INVALID;
+	return RSX_OK;
+}
+
+int rsx_split_counts(const void *src, size_t n, const rsx_layout *layout, const uint64_t *splitters, int nsplit,
+                     uint64_t *counts_out, void *stream) {
+	KeyDesc kd;
+	int r = check_layout(layout, &kd);
+	if (r || (r = check_splitters(splitters, nsplit)))
+		return r;
+	if (!counts_out || (n && !src))
+		return RSX_ERR_INVALID;
+	int dev;
+	if ((r = current_device(&dev)))
+		return r;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	unsigned long long *d = nullptr, h[16] = {};
+	CU(cudaMalloc((void **)&d, 32 * sizeof(unsigned long long)));
+	cudaError_t e = cudaMemsetAsync(d, 0, 32 * sizeof(unsigned long long), st);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(d + 16, splitters, sizeof(uint64_t) * nsplit, cudaMemcpyHostToDevice, st);
+	if (e == cudaSuccess && n)
+		e = launch_split_counts(src, n, layout->record_bytes, kd, d + 16, (uint32_t)nsplit, d, g_dev[dev].num_sms, st);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(st);
+	cudaFree(d);
+	if (e != cudaSuccess)
+		return fail_cuda(e, "rsx_split_counts");
+	for (int j = 0; j <= nsplit; ++j)
+		counts_out[j] = h[j];
+	return RSX_OK;
+}
+
+int rsx_split_pass_to(const void *src, size_t n, const rsx_layout *layout, const uint64_t *splitters, int nsplit,
+                      const uint64_t *dest_base, void *stream) {
+	KeyDesc kd;
+	int r = check_layout(layout, &kd);
+	if (r || (r = check_splitters(splitters, nsplit)))
+		return r;
+	if (!src || !dest_base || n < 1)
+		return RSX_ERR_INVALID;
+	int dev;
+	if ((r = current_device(&dev)))
+		return r;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	Plan P;
+	make_plan(P, n, layout, kd, 0, 0);
+	Lease L;
+	if ((r = acquire(L, dev, P.total)))
+		return r;
+	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
+	const int sms = g_dev[dev].num_sms;
+	// no histogram needed: destinations get explicit base addresses; only the look-back state and
+	// the tile ticket have to be zero
+	CU(cudaMemsetAsync(wsp, 0, kWsZeroBytes, st));
+	CU(cudaMemsetAsync(wsp + P.off_status, 0, P.status_bytes_per_col, st));
+	unsigned char owner[kBins];
+	for (int b = 0; b < kBins; ++b)
+		owner[b] = (unsigned char)(b <= nsplit ? b : nsplit); // "digit" == destination
+	CU(cudaMemcpyAsync(ws->dest_base, dest_base, sizeof(uint64_t) * (nsplit + 1), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ws->owner, owner, kBins, cudaMemcpyHostToDevice, st));
+	PassBuffers pb{};
+	pb.rec_first = src;
+	CU(launch_scatter(pb, P.n, P.rb, 0, P.kd, 0, ws, true, wsp + P.off_status, &ws->tickets[0], P.wide, sms, st,
+	                  ws->dest_base, ws->owner, reinterpret_cast<const unsigned long long *>(splitters), nsplit));
 	CU(cudaStreamSynchronize(st));
 	return RSX_OK;
 }

@@ -86,7 +86,8 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
                            const KeyDesc &kd, int col, const WsHead *ws_offsets /*offs + ctl*/,
                            bool forced, void *status, unsigned int *ticket, bool wide_offsets,
                            int num_sms, cudaStream_t st, const unsigned long long *dest_base = nullptr,
-                           const unsigned char *owner = nullptr);
+                           const unsigned char *owner = nullptr, const unsigned long long *splitters = nullptr,
+                           int nsplit = 0);
 
 PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes);
 
@@ -95,6 +96,11 @@ cudaError_t launch_iota_if_early(void *index_buffer, int idx_bytes, size_t n, co
                                  cudaStream_t st);
 cudaError_t launch_narrow_index(const uint32_t *wide0, const uint32_t *wide1, void *index_buffer,
                                 int idx_bytes, size_t n, const Ctl *ctl, cudaStream_t st);
+
+// key-range routing counts (d_counts: 16 zeroed entries)
+cudaError_t launch_split_counts(const void *data, size_t n, uint32_t record_bytes, const KeyDesc &kd,
+                                const unsigned long long *d_split, uint32_t nsplit, unsigned long long *d_counts,
+                                int num_sms, cudaStream_t st);
 
 // hardware probe for the ticket ranking (see rsx_scatter.cuh); *d_mismatch must be zeroed
 cudaError_t launch_ticket_probe(unsigned long long *d_mismatch, int num_sms, cudaStream_t st);

@@ -39,6 +39,8 @@
 
 namespace rsx {
 
+constexpr int kMaxSplit = 15; // up to 16 destinations for key-range routing
+
 struct ScatterParams {
 	PassBuffers pb;
 	size_t n;
@@ -58,7 +60,27 @@ struct ScatterParams {
 	// across tiles (the receiver's LSD sort does not need that).  Records only (no payload).
 	const unsigned long long *dest_base; // device memory, one byte address per destination
 	const unsigned char *owner;          // device memory, 256 entries
+	// Key-range routing (DIGIT_SPLIT): the "digit" of a record is the number of splitters that are
+	// <= its derived key, i.e. its destination among nsplit + 1 key ranges.
+	KeyDesc kd;
+	uint32_t nsplit;
+	unsigned long long split[kMaxSplit];
 };
+
+enum { DIGIT_PLAIN = 0, DIGIT_FLOAT = 1, DIGIT_SPLIT = 2 };
+
+template <int ES, int DM>
+__device__ __forceinline__ uint32_t tile_digit(const ScatterParams &p, const typename Rec<ES>::type &r, const DigitDesc &dd) {
+	if constexpr (DM == DIGIT_SPLIT) {
+		const unsigned long long k = derive_key(key_word<ES>(r, p.kd.word_sel), p.kd);
+		uint32_t d = 0;
+		for (uint32_t j = 0; j < p.nsplit; ++j)
+			d += k >= p.split[j];
+		return d;
+	} else {
+		return digit_of<ES, DM == DIGIT_FLOAT>(r, dd);
+	}
+}
 
 #ifdef RSX_PHASE_TIMING
 #define RSX_T(k)                                                    \
@@ -182,7 +204,7 @@ template <int ES, int PL, class Cfg> struct ScatterSmem {
 
 enum { RANK_TICKET = 0, RANK_BALLOT = 1 };
 
-template <int ES, int PL, bool FLOAT, typename OffT, int RANK, class Cfg>
+template <int ES, int PL, int DM, typename OffT, int RANK, class Cfg>
 __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel(const ScatterParams p) {
 	using R = typename Rec<ES>::type;
 	using P = typename Payload<PL>::type;
@@ -316,7 +338,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 			uint32_t hotcnt = 0;
 #pragma unroll
 			for (int i = 0; i < ITEMS; ++i) {
-				const uint32_t d = digit_of<ES, FLOAT>(s_stage[t0 + i * 32], dd);
+				const uint32_t d = tile_digit<ES, DM>(p, s_stage[t0 + i * 32], dd);
 				const bool is_hot = d == hot;
 				const uint32_t m = __ballot_sync(FULL, is_hot);
 				if (is_hot)
@@ -330,7 +352,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		} else {
 #pragma unroll
 			for (int i = 0; i < ITEMS; ++i) {
-				const uint32_t d = digit_of<ES, FLOAT>(s_stage[t0 + i * 32], dd);
+				const uint32_t d = tile_digit<ES, DM>(p, s_stage[t0 + i * 32], dd);
 				uint32_t peers = FULL;
 #pragma unroll
 				for (int b = 0; b < 8; ++b) {
@@ -402,7 +424,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 #pragma unroll
 		for (int i = 0; i < ITEMS; ++i) {
 			const R r = s_stage[t0 + i * 32];
-			const uint32_t pos = wh[digit_of<ES, FLOAT>(r, dd)] + rank[i];
+			const uint32_t pos = wh[tile_digit<ES, DM>(p, r, dd)] + rank[i];
 			s_rec[pos] = r;
 			if constexpr (PL != 0)
 				s_pl[pos] = synth ? (P)(base + t0 + i * 32) : s_stage_pl[t0 + i * 32];
@@ -513,7 +535,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		if (p.dest_base != nullptr) { // straight into the owner's buffer (peer memory over NVLink)
 			for (uint32_t s = tid; s < valid; s += THREADS) {
 				const R r = s_rec[s];
-				R *dst = reinterpret_cast<R *>(s_gptr[digit_of<ES, FLOAT>(r, dd)]) + s;
+				R *dst = reinterpret_cast<R *>(s_gptr[tile_digit<ES, DM>(p, r, dd)]) + s;
 				*dst = r;
 			}
 		} else if (full) {
@@ -521,7 +543,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 			for (int i = 0; i < ITEMS; ++i) {
 				const uint32_t s = tid + i * THREADS;
 				const R r = s_rec[s];
-				const OffT g = s_gadj[digit_of<ES, FLOAT>(r, dd)] + (OffT)s;
+				const OffT g = s_gadj[tile_digit<ES, DM>(p, r, dd)] + (OffT)s;
 				if (write_rec)
 					out[g] = r;
 				if constexpr (PL != 0)
@@ -530,7 +552,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		} else {
 			for (uint32_t s = tid; s < valid; s += THREADS) {
 				const R r = s_rec[s];
-				const OffT g = s_gadj[digit_of<ES, FLOAT>(r, dd)] + (OffT)s;
+				const OffT g = s_gadj[tile_digit<ES, DM>(p, r, dd)] + (OffT)s;
 				if (write_rec)
 					out[g] = r;
 				if constexpr (PL != 0)
@@ -550,10 +572,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 #endif
 }
 
-template <int ES, int PL, bool FLOAT, typename OffT, int RANK, class Cfg>
+template <int ES, int PL, int DM, typename OffT, int RANK, class Cfg>
 cudaError_t launch_scatter_c(const ScatterParams &sp, int num_sms, cudaStream_t st) {
 	using SM = ScatterSmem<ES, PL, Cfg>;
-	auto kern = scatter_kernel<ES, PL, FLOAT, OffT, RANK, Cfg>;
+	auto kern = scatter_kernel<ES, PL, DM, OffT, RANK, Cfg>;
 	static int occ_cache[64] = {}; // per device
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -578,38 +600,45 @@ cudaError_t launch_scatter_c(const ScatterParams &sp, int num_sms, cudaStream_t 
 	return cudaGetLastError();
 }
 
-template <int ES, int PL, bool FLOAT, typename OffT, int RANK>
+template <int ES, int PL, int DM, typename OffT, int RANK>
 cudaError_t launch_scatter_r(const ScatterParams &sp, int num_sms, cudaStream_t st) {
-	if constexpr ((ES == 4 || ES == 8) && PL == 0 && !FLOAT && RANK == RANK_TICKET && sizeof(OffT) == 4) {
+	if constexpr ((ES == 4 || ES == 8) && PL == 0 && DM == DIGIT_PLAIN && RANK == RANK_TICKET && sizeof(OffT) == 4) {
 		switch (scatter_variant()) {
-		case 1: return launch_scatter_c<ES, PL, FLOAT, OffT, RANK, ScatterCfgV<ES, PL, 1>>(sp, num_sms, st);
-		case 2: return launch_scatter_c<ES, PL, FLOAT, OffT, RANK, ScatterCfgV<ES, PL, 2>>(sp, num_sms, st);
-		case 3: return launch_scatter_c<ES, PL, FLOAT, OffT, RANK, ScatterCfgV<ES, PL, 3>>(sp, num_sms, st);
-		case 4: return launch_scatter_c<ES, PL, FLOAT, OffT, RANK, ScatterCfgV<ES, PL, 4>>(sp, num_sms, st);
-		case 5: return launch_scatter_c<ES, PL, FLOAT, OffT, RANK, ScatterCfgV<ES, PL, 5>>(sp, num_sms, st);
+		case 1: return launch_scatter_c<ES, PL, DM, OffT, RANK, ScatterCfgV<ES, PL, 1>>(sp, num_sms, st);
+		case 2: return launch_scatter_c<ES, PL, DM, OffT, RANK, ScatterCfgV<ES, PL, 2>>(sp, num_sms, st);
+		case 3: return launch_scatter_c<ES, PL, DM, OffT, RANK, ScatterCfgV<ES, PL, 3>>(sp, num_sms, st);
+		case 4: return launch_scatter_c<ES, PL, DM, OffT, RANK, ScatterCfgV<ES, PL, 4>>(sp, num_sms, st);
+		case 5: return launch_scatter_c<ES, PL, DM, OffT, RANK, ScatterCfgV<ES, PL, 5>>(sp, num_sms, st);
 		default: break;
 		}
 	}
-	return launch_scatter_c<ES, PL, FLOAT, OffT, RANK, ScatterCfg<ES, PL>>(sp, num_sms, st);
+	return launch_scatter_c<ES, PL, DM, OffT, RANK, ScatterCfg<ES, PL>>(sp, num_sms, st);
 }
 
-template <int ES, int PL, bool FLOAT, typename OffT>
+template <int ES, int PL, int DM, typename OffT>
 cudaError_t launch_scatter_t(const ScatterParams &sp, int num_sms, cudaStream_t st) {
-	return rank_mode() == RANK_TICKET ? launch_scatter_r<ES, PL, FLOAT, OffT, RANK_TICKET>(sp, num_sms, st)
-	                                  : launch_scatter_r<ES, PL, FLOAT, OffT, RANK_BALLOT>(sp, num_sms, st);
+	return rank_mode() == RANK_TICKET ? launch_scatter_r<ES, PL, DM, OffT, RANK_TICKET>(sp, num_sms, st)
+	                                  : launch_scatter_r<ES, PL, DM, OffT, RANK_BALLOT>(sp, num_sms, st);
 }
 
 template <int ES, int PL>
 cudaError_t launch_scatter_pl(const ScatterParams &sp, bool is_float, bool wide, int num_sms, cudaStream_t st) {
+	if (sp.nsplit != 0) { // routing by key-range splitters (multi-GPU partition): records only
+		if constexpr (PL == 0)
+			return wide ? launch_scatter_t<ES, PL, DIGIT_SPLIT, unsigned long long>(sp, num_sms, st)
+			            : launch_scatter_t<ES, PL, DIGIT_SPLIT, uint32_t>(sp, num_sms, st);
+		else
+			return cudaErrorInvalidValue;
+	}
 	if constexpr (ES == 4 || ES == 8) {
 		if (is_float)
-			return wide ? launch_scatter_t<ES, PL, true, unsigned long long>(sp, num_sms, st)
-			            : launch_scatter_t<ES, PL, true, uint32_t>(sp, num_sms, st);
+			return wide ? launch_scatter_t<ES, PL, DIGIT_FLOAT, unsigned long long>(sp, num_sms, st)
+			            : launch_scatter_t<ES, PL, DIGIT_FLOAT, uint32_t>(sp, num_sms, st);
 	}
 	if (is_float)
 		return cudaErrorInvalidValue;
-	return wide ? launch_scatter_t<ES, PL, false, unsigned long long>(sp, num_sms, st)
-	            : launch_scatter_t<ES, PL, false, uint32_t>(sp, num_sms, st);
+	return wide ? launch_scatter_t<ES, PL, DIGIT_PLAIN, unsigned long long>(sp, num_sms, st)
+	            : launch_scatter_t<ES, PL, DIGIT_PLAIN, uint32_t>(sp, num_sms, st);
 }
 
 template <int ES>

@@ -90,6 +90,43 @@ __global__ void verify_kernel(const typename Rec<ES>::type *__restrict__ data, s
 	}
 }
 
+// Key-range routing: counts[j] = number of records whose derived key falls in range j, where the
+// range index is the number of splitters <= key (splitters ascending).  One read of the records.
+template <int ES>
+__global__ void split_counts_kernel(const typename Rec<ES>::type *__restrict__ data, size_t n, KeyDesc kd,
+                                    const unsigned long long *__restrict__ split, uint32_t nsplit,
+                                    unsigned long long *counts) {
+	__shared__ unsigned long long s_split[16];
+	__shared__ unsigned int s_cnt[16];
+	if (threadIdx.x < 16) {
+		s_split[threadIdx.x] = threadIdx.x < nsplit ? split[threadIdx.x] : ~0ULL;
+		s_cnt[threadIdx.x] = 0;
+	}
+	__syncthreads();
+	uint32_t local[16];
+#pragma unroll
+	for (int j = 0; j < 16; ++j)
+		local[j] = 0;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const unsigned long long k = derive_key(key_word<ES>(data[i], kd.word_sel), kd);
+		uint32_t d = 0;
+		for (uint32_t j = 0; j < nsplit; ++j)
+			d += k >= s_split[j];
+#pragma unroll
+		for (int j = 0; j < 16; ++j)
+			local[j] += (d == (uint32_t)j);
+	}
+#pragma unroll
+	for (int j = 0; j < 16; ++j) {
+		const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, local[j]);
+		if ((threadIdx.x & 31) == 0 && v)
+			atomicAdd(&s_cnt[j], v);
+	}
+	__syncthreads();
+	if (threadIdx.x < 16 && s_cnt[threadIdx.x])
+		atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+
 // Hardware probe behind RANK_TICKET (rsx_scatter.cuh): are same-address shared-memory atomicAdd
 // tickets of one warp instruction handed out in ascending lane order, and a warp's back-to-back
 // atomics applied in program order?  Compared against the ballot-derived stable rank.
@@ -146,6 +183,22 @@ inline int grid_for(size_t n, int threads, int cap) {
 }
 
 } // namespace
+
+cudaError_t launch_split_counts(const void *data, size_t n, uint32_t record_bytes, const KeyDesc &kd,
+                                const unsigned long long *d_split, uint32_t nsplit, unsigned long long *d_counts,
+                                int num_sms, cudaStream_t st) {
+	const int g = grid_for(n, 512, num_sms * 4);
+	switch (record_bytes) {
+	case 1: split_counts_kernel<1><<<g, 512, 0, st>>>(static_cast<const uint8_t *>(data), n, kd, d_split, nsplit, d_counts); break;
+	case 2: split_counts_kernel<2><<<g, 512, 0, st>>>(static_cast<const uint16_t *>(data), n, kd, d_split, nsplit, d_counts); break;
+	case 4: split_counts_kernel<4><<<g, 512, 0, st>>>(static_cast<const uint32_t *>(data), n, kd, d_split, nsplit, d_counts); break;
+	case 8: split_counts_kernel<8><<<g, 512, 0, st>>>(static_cast<const unsigned long long *>(data), n, kd, d_split, nsplit, d_counts); break;
+	case 16: split_counts_kernel<16><<<g, 512, 0, st>>>(static_cast<const ulonglong2 *>(data), n, kd, d_split, nsplit, d_counts); break;
+	default: return cudaErrorInvalidValue;
+	}
+	count_launch();
+	return cudaGetLastError();
+}
 
 cudaError_t launch_ticket_probe(unsigned long long *d_mismatch, int num_sms, cudaStream_t st) {
 	for (uint32_t mask : {0xFFu, 0x0Fu, 0x01u, 0x00u})

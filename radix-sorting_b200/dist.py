@@ -100,6 +100,32 @@ class CudaEngine:
     def scatter_pass_to(self, src, col, owner, dest_base, kf):
         self.rsx.scatter_pass_to(src, col, owner, dest_base, kf)
 
+    # ---- key-range routing (skewed inputs) -------------------------------------------------------
+    def sample_keys(self, keys, kf, count) -> np.ndarray:
+        """`count` evenly spaced records' DERIVED keys (uint64)."""
+        L = kf.layout(keys.element_size())
+        n = keys.numel() * keys.element_size() // L.record_bytes
+        raw = keys.view(self.torch.uint8).view(n, L.record_bytes)
+        idx = self.torch.linspace(0, n - 1, steps=min(count, n), device=keys.device).to(self.torch.int64)
+        return derive_np(raw[idx].cpu().numpy(), L)
+
+    def split_counts(self, keys, splitters, kf):
+        return self.rsx.split_counts(keys, splitters, kf)
+
+    def split_pass_to(self, keys, splitters, dest_base, kf):
+        self.rsx.split_pass_to(keys, splitters, dest_base, kf)
+
+    def split_partition(self, keys, splitters, counts, kf):
+        """Local stable partition by key range (the non-fused form): returns the grouped copy."""
+        L = kf.layout(keys.element_size())
+        part = self.empty(keys.numel(), keys)
+        base, acc = [], 0
+        for c in counts:
+            base.append(part.data_ptr() + acc * L.record_bytes)
+            acc += c
+        self.rsx.split_pass_to(keys, splitters, base, kf)
+        return part
+
     def empty(self, n, like):
         return self.torch.empty(n, dtype=like.dtype, device=like.device)
 
@@ -113,6 +139,29 @@ def derive_key_py(record: bytes, L) -> int:
     elif L.kdf_kind == 2:
         k ^= m if k & top else top
     return (~k & m) if (L.flags & 1) else k
+
+
+def derive_np(records: np.ndarray, L) -> np.ndarray:
+    """Vectorised derived keys (uint64) of an (n, record_bytes) uint8 array."""
+    kb = L.key_bytes
+    k = np.zeros(records.shape[0], dtype=np.uint64)
+    for b in range(kb):
+        k |= records[:, L.key_offset + b].astype(np.uint64) << np.uint64(8 * b)
+    m = np.uint64((1 << (8 * kb)) - 1) if kb < 8 else np.uint64(0xFFFFFFFFFFFFFFFF)
+    top = np.uint64(1 << (8 * kb - 1))
+    if L.kdf_kind == 1:
+        k ^= top
+    elif L.kdf_kind == 2:
+        k = np.where(k & top, k ^ m, k ^ top)
+    if L.flags & 1:
+        k = ~k & m
+    return k
+
+
+def choose_splitters(samples: np.ndarray, world: int):
+    """world - 1 ascending derived-key splitters at the quantiles of the pooled samples."""
+    srt = np.sort(samples.astype(np.uint64))
+    return [int(srt[min(len(srt) - 1, (i * len(srt)) // world)]) for i in range(1, world)]
 
 
 def assign_buckets(global_counts: np.ndarray, world: int) -> np.ndarray:
@@ -141,7 +190,66 @@ class PartitionInfo:
     seconds: dict
 
 
-def partitioned_sort(keys, kf, group=None, engine=None, timers: bool = False, fused: bool = True):
+def _sort_by_key_ranges(keys, kf, L, group, engine, world, rank, dev, live, n_total, n_local, rec_elems, fused,
+                        sec, tick, t):
+    import torch
+    import torch.distributed as dist
+    samples = engine.sample_keys(keys, kf, 8192) if n_local else np.zeros(0, dtype=np.uint64)
+    pad = np.full(8192, np.iinfo(np.uint64).max, dtype=np.uint64)  # ragged shards: fixed-size exchange
+    pad[: len(samples)] = samples
+    mine = torch.from_numpy(np.concatenate([[len(samples)], pad.view(np.int64)]).astype(np.int64)).to(dev)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    pooled = np.concatenate([g.cpu().numpy()[1:1 + int(g[0])].view(np.uint64) for g in gathered])
+    splitters = choose_splitters(pooled, world)
+    counts = engine.split_counts(keys, splitters, kf) if n_local else [0] * world
+    cmine = torch.tensor(counts, dtype=torch.int64, device=dev)
+    call = [torch.empty_like(cmine) for _ in range(world)]
+    dist.all_gather(call, cmine, group=group)
+    cnt = torch.stack(call).cpu().numpy()  # [source][destination]
+    send = [int(c) for c in cnt[rank]]
+    recv = [int(c) for c in cnt[:, rank]]
+    n_out = sum(recv)
+    t = tick("sample+split_counts", t)
+    symm = None
+    if fused and hasattr(engine, "symmetric_recv"):
+        cap = int(cnt.sum(axis=0).max()) * rec_elems
+        symm = engine.symmetric_recv(max(cap, 1), keys, group)
+        ok = torch.tensor([1 if symm is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if not int(ok.item()):
+            symm = None
+    if symm is not None:
+        out_buf, bases, handle = symm
+        dest_base = [bases[d] + int(cnt[:rank, d].sum()) * L.record_bytes for d in range(world)]
+        handle.barrier()
+        if n_local:
+            engine.split_pass_to(keys, splitters, dest_base, kf)
+        torch.cuda.synchronize(dev)
+        handle.barrier()
+        t = tick("fused_partition_exchange", t)
+    else:
+        part = engine.split_partition(keys, splitters, counts, kf) if n_local else keys
+        t = tick("partition_pass", t)
+        out_buf = engine.empty(max(n_out, 1) * rec_elems, keys)
+        dist.all_to_all_single(out_buf[: n_out * rec_elems], part, [r * rec_elems for r in recv],
+                               [s * rec_elems for s in send], group=group)
+        t = tick("all_to_all", t)
+        del part
+    recv_view = out_buf[: n_out * rec_elems]
+    if n_out > 1:
+        aux = keys if keys.numel() >= recv_view.numel() else engine.empty(recv_view.numel(), keys)
+        res = engine.sort(recv_view, aux[: recv_view.numel()], kf)
+    else:
+        res = recv_view
+    t = tick("local_sort", t)
+    sec["exchange"] = ("fused peer stores (NVLink)" if symm is not None else "all_to_all_single") + ", key-range routing"
+    info = PartitionInfo(-1, live, send, recv, n_out, n_total, n_out / max(n_total / world, 1), sec)
+    return res, info
+
+
+def partitioned_sort(keys, kf, group=None, engine=None, timers: bool = False, fused: bool = True,
+                     skew_threshold: float = 1.15):
     """Globally sorts the concatenation (in rank order) of every rank's `keys`.
     Returns (this rank's slice of the sorted sequence, PartitionInfo).  `keys` is clobbered."""
     import torch
@@ -183,11 +291,18 @@ def partitioned_sort(keys, kf, group=None, engine=None, timers: bool = False, fu
         return out, info
     top = live[-1]
     owner = assign_buckets(total[top], world)
+    rec_elems = L.record_bytes // keys.element_size()
+    predicted = max(int(total[top][owner == d].sum()) for d in range(world)) / max(n_total / world, 1)
+    if predicted > skew_threshold and hasattr(engine, "split_counts") and world - 1 <= 15:
+        # Skewed routing digit (e.g. zipf: most of the mass in one top bucket): bucket-granular
+        # ranges cannot balance, so route by key range instead -- splitters at the quantiles of a
+        # pooled sample (sample sort); exact per-destination counts from one counting pass.
+        return _sort_by_key_ranges(keys, kf, L, group, engine, world, rank, dev, live, n_total, n_local,
+                                   rec_elems, fused, sec, tick, t)
     send = [int(per_rank[rank, top, owner == d].sum()) for d in range(world)]
     recv = [int(per_rank[s, top, owner == rank].sum()) for s in range(world)]
     n_out = sum(recv)
 
-    rec_elems = L.record_bytes // keys.element_size()
     symm = None
     if fused and hasattr(engine, "symmetric_recv"):
         # every rank must take the same branch: capacity is the global maximum, known to all

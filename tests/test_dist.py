@@ -51,6 +51,25 @@ class OracleEngine:
     def empty(self, n, like):
         return torch.empty(n, dtype=like.dtype)
 
+    # key-range routing (skewed inputs)
+    def _derived(self, keys):
+        dsort = importlib.import_module("radix-sorting_b200.dist")
+        a = self._np(keys)
+        return dsort.derive_np(a.view(np.uint8).reshape(a.shape[0], self.t.record_bytes), self.t.layout())
+
+    def sample_keys(self, keys, kf, count):
+        d = self._derived(keys)
+        idx = np.linspace(0, len(d) - 1, num=min(count, len(d))).astype(np.int64)
+        return d[idx]
+
+    def split_counts(self, keys, splitters, kf):
+        dest = np.searchsorted(np.array(splitters, dtype=np.uint64), self._derived(keys), side="right")
+        return [int((dest == j).sum()) for j in range(len(splitters) + 1)]
+
+    def split_partition(self, keys, splitters, counts, kf):
+        dest = np.searchsorted(np.array(splitters, dtype=np.uint64), self._derived(keys), side="right")
+        return keys[torch.from_numpy(np.argsort(dest, kind="stable"))].clone()
+
 
 def _worker(rank, world, port, tname, n_per, dist_name, mask, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -108,6 +127,16 @@ def test_partitioned_sort_world3_ragged_and_skipped_columns():
     outs = _run(3, "u64", [0, 1000, 1001, 5000], mask=0x0000000000FFFFFF)
     assert outs[0][3] == 2
     _run(3, "u32", [0, 10, 2000, 2500], dist_name="zipf")
+
+
+def test_partitioned_sort_skewed_keys_use_key_range_routing():
+    """zipf keys: most of the mass sits in one bucket of the routing digit, so the sort switches to
+    sample-based key-range splitters; the result is still bit-identical and roughly balanced."""
+    outs = _run(3, "u32", [0, 4000, 8000, 12000], dist_name="zipf")
+    assert all(o[3] == -1 for o in outs)
+    assert max(o[4] for o in outs) < 1.35
+    outs = _run(2, "u64", [0, 3000, 9000], dist_name="zipf")
+    assert all(o[3] == -1 for o in outs)
 
 
 def test_partitioned_sort_constant_and_presorted():

@@ -405,3 +405,27 @@ def test_more_than_2_pow_32_records(rsx, torch):
     assert rep.ncols == 1 and res.data_ptr() == aux.data_ptr()
     hist, descents, _ = rsx.histogram(res, kf)
     assert int(hist.sum()) == n and descents == 0
+
+
+@pytest.mark.parametrize("tname", ["u32", "u64", "i64", "f32", "rec8_u32"])
+def test_key_range_routing(rsx, torch, oracle, tname):
+    """rsx_split_counts / rsx_split_pass_to: destination = number of splitters <= derived key."""
+    import importlib
+    dsort = importlib.import_module("radix-sorting_b200.dist")
+    t = TYPES[tname]
+    n = 200003
+    data = make_input(tname, n, 77, "zipf" if tname in ("u32", "u64", "rec8_u32") else "uniform")
+    L = t.layout()
+    derived = dsort.derive_np(np.ascontiguousarray(data).view(np.uint8).reshape(n, t.record_bytes), L)
+    splitters = dsort.choose_splitters(derived[::37], 5)
+    dest = np.searchsorted(np.array(splitters, dtype=np.uint64), derived, side="right")
+    src = to_dev(torch, data)
+    kf = kf_for(rsx, tname)
+    counts = rsx.split_counts(src, splitters, kf)
+    assert counts == [int((dest == j).sum()) for j in range(5)]
+    bufs = [torch.full((max(c, 1) * t.record_bytes,), 0xAB, dtype=torch.uint8, device="cuda") for c in counts]
+    rsx.split_pass_to(src, splitters, [b.data_ptr() for b in bufs], kf)
+    torch.cuda.synchronize()
+    for j in range(5):
+        got = bufs[j][: counts[j] * t.record_bytes].cpu().numpy()
+        assert got.tobytes() == data[dest == j].tobytes(), f"range {j}: not the stable sub-sequence"
