@@ -106,7 +106,8 @@ class CudaEngine:
         L = kf.layout(keys.element_size())
         n = keys.numel() * keys.element_size() // L.record_bytes
         raw = keys.view(self.torch.uint8).view(n, L.record_bytes)
-        idx = self.torch.linspace(0, n - 1, steps=min(count, n), device=keys.device).to(self.torch.int64)
+        c = min(count, n)
+        idx = (self.torch.arange(c, device=keys.device, dtype=self.torch.int64) * n) // c  # exact integer stride
         return derive_np(raw[idx].cpu().numpy(), L)
 
     def split_counts(self, keys, splitters, kf):
