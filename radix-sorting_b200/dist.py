@@ -130,6 +130,20 @@ class CudaEngine:
     def empty(self, n, like):
         return self.torch.empty(n, dtype=like.dtype, device=like.device)
 
+    _scratch = {}
+
+    def scratch(self, n, like):
+        """Grow-only cached buffer (the local sort's aux): no allocator traffic in steady state.
+        Like the receive buffer it is owned by the engine and reused by the next call."""
+        key = (like.dtype, like.device.index)
+        cur = self._scratch.get(key)
+        if cur is None or cur.numel() < n:
+            cur = None
+            self._scratch[key] = None
+            cur = self.torch.empty(int(n * 1.05) + 1024, dtype=like.dtype, device=like.device)
+            self._scratch[key] = cur
+        return cur[:n]
+
 
 def derive_key_py(record: bytes, L) -> int:
     """Derived key of ONE record (radix_sort_basic_kdf.hpp:19-46) -- used for 1-element shards only."""
@@ -239,7 +253,8 @@ def _sort_by_key_ranges(keys, kf, L, group, engine, world, rank, dev, live, n_to
         del part
     recv_view = out_buf[: n_out * rec_elems]
     if n_out > 1:
-        aux = keys if keys.numel() >= recv_view.numel() else engine.empty(recv_view.numel(), keys)
+        aux = keys if keys.numel() >= recv_view.numel() else (
+            engine.scratch(recv_view.numel(), keys) if hasattr(engine, "scratch") else engine.empty(recv_view.numel(), keys))
         res = engine.sort(recv_view, aux[: recv_view.numel()], kf)
     else:
         res = recv_view
@@ -340,7 +355,8 @@ def partitioned_sort(keys, kf, group=None, engine=None, timers: bool = False, fu
     # 6. local LSD sort of the received records (chunks arrive in source-rank order: stable)
     recv_view = out_buf[: n_out * rec_elems]
     if n_out > 1:
-        aux = keys if keys.numel() >= recv_view.numel() else engine.empty(recv_view.numel(), keys)
+        aux = keys if keys.numel() >= recv_view.numel() else (
+            engine.scratch(recv_view.numel(), keys) if hasattr(engine, "scratch") else engine.empty(recv_view.numel(), keys))
         res = engine.sort(recv_view, aux[: recv_view.numel()], kf)
     else:
         res = recv_view
@@ -465,7 +481,8 @@ def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world
                    "imbalance_max_over_mean": max(n_outs) / (n_total / world), "verified": verified,
                    "timing": "CUDA events per rank around partitioned_sort, all_reduce MAX over ranks, mean of steps",
                    "l2": "inputs larger than L2, restored before every step",
-                   "phase_seconds_rank0": info_t.seconds, "symm_error": CudaEngine.symm_error},
+                   "phase_seconds_rank0": info_t.seconds, "symm_error": CudaEngine.symm_error,
+                   "ms_steps": [round(x, 3) for x in times]},
         "roofline": {"bound": "hbm", "kernel": "whole partitioned sort, per GPU", "achieved": moved / (ms_per_step * 1e-3) / 1e9,
                      "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
                      "note": "per-GPU algorithmic HBM bytes (histogram + partition pass + local LSD) over the step time; "
