@@ -429,3 +429,18 @@ def test_key_range_routing(rsx, torch, oracle, tname):
     for j in range(5):
         got = bufs[j][: counts[j] * t.record_bytes].cpu().numpy()
         assert got.tobytes() == data[dest == j].tobytes(), f"range {j}: not the stable sub-sequence"
+
+
+def test_multipass_composite_key_like_listing5(rsx, torch, oracle):
+    """radix_sort_u64_multipass.c:117-118 sorts a 64-bit key with two stable 32-bit sorts (low half,
+    then high half).  The same composition through key_offset/key_bytes windows must equal one
+    64-bit sort -- this is what makes keys wider than 64 bits sortable."""
+    n = 300001
+    data = make_input("rec16_u64", n, 41, "and2")
+    src = to_dev(torch, data)
+    aux = torch.zeros_like(src)
+    lo = rsx.radix_sort(src, aux, None, rsx.KeyFunc(rsx.KDF_UNSIGNED, False, 16, 0, 4))
+    other = aux if lo.data_ptr() == src.data_ptr() else src
+    hi = rsx.radix_sort(lo, other, None, rsx.KeyFunc(rsx.KDF_UNSIGNED, False, 16, 4, 4))
+    want, _, _ = oracle.radix_sort(data, TYPES["rec16_u64"].layout())
+    assert hi.cpu().numpy().tobytes() == want.tobytes()
