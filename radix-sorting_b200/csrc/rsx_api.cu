@@ -413,7 +413,7 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
                            const KeyDesc &kd, int col, const WsHead *ws, bool forced, void *status,
                            unsigned int *ticket, bool wide, int num_sms, cudaStream_t st,
                            const unsigned long long *dest_base, const unsigned char *owner,
-                           const unsigned long long *splitters, int nsplit) {
+                           const unsigned long long *splitters, int nsplit, int ndest) {
 	ScatterParams sp;
 	sp.pb = pb;
 	sp.n = n;
@@ -431,6 +431,7 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
 	sp.dbg = nullptr;
 	sp.dest_base = dest_base;
 	sp.owner = owner;
+	sp.ndest = (uint32_t)ndest;
 	sp.kd = kd;
 	sp.nsplit = (uint32_t)nsplit;
 	for (int j = 0; j < kMaxSplit; ++j)
@@ -877,7 +878,7 @@ int rsx_scatter_pass_to(const void *src, size_t n, const rsx_layout *layout, int
 	PassBuffers pb{};
 	pb.rec_first = src;
 	CU(launch_scatter(pb, P.n, P.rb, 0, P.kd, col, ws, true, wsp + P.off_status, &ws->tickets[col], P.wide, sms, st,
-	                  ws->dest_base, ws->owner));
+	                  ws->dest_base, ws->owner, nullptr, 0, ndest));
 	CU(cudaStreamSynchronize(st));
 	return RSX_OK;
 }
@@ -955,7 +956,7 @@ int rsx_split_pass_to(const void *src, size_t n, const rsx_layout *layout, const
 	PassBuffers pb{};
 	pb.rec_first = src;
 	CU(launch_scatter(pb, P.n, P.rb, 0, P.kd, 0, ws, true, wsp + P.off_status, &ws->tickets[0], P.wide, sms, st,
-	                  ws->dest_base, ws->owner, reinterpret_cast<const unsigned long long *>(splitters), nsplit));
+	                  ws->dest_base, ws->owner, reinterpret_cast<const unsigned long long *>(splitters), nsplit, nsplit + 1));
 	CU(cudaStreamSynchronize(st));
 	return RSX_OK;
 }

@@ -87,7 +87,7 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
                            bool forced, void *status, unsigned int *ticket, bool wide_offsets,
                            int num_sms, cudaStream_t st, const unsigned long long *dest_base = nullptr,
                            const unsigned char *owner = nullptr, const unsigned long long *splitters = nullptr,
-                           int nsplit = 0);
+                           int nsplit = 0, int ndest = 0);
 
 PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes);
 

@@ -60,6 +60,7 @@ struct ScatterParams {
 	// across tiles (the receiver's LSD sort does not need that).  Records only (no payload).
 	const unsigned long long *dest_base; // device memory, one byte address per destination
 	const unsigned char *owner;          // device memory, 256 entries
+	uint32_t ndest;
 	// Key-range routing (DIGIT_SPLIT): the "digit" of a record is the number of splitters that are
 	// <= its derived key, i.e. its destination among nsplit + 1 key ranges.
 	KeyDesc kd;
@@ -194,17 +195,18 @@ template <int ES, int PL, class Cfg> struct ScatterSmem {
 	static constexpr size_t kAdjBytes = (size_t)kBins * 8;
 	// layout: [stage rec | stage pl | sorted rec | sorted pl | warp counters | gadj | misc]
 	static constexpr size_t kOffSorted = kStageBytes;
-	static constexpr size_t kOffWh = kOffSorted + kRecBytes + kPlBytes;
+	static constexpr size_t kSortedSlack = 32; // fused mode reads one 16-byte vector past a run's last chunk
+	static constexpr size_t kOffWh = kOffSorted + kRecBytes + kSortedSlack + kPlBytes;
 	static constexpr size_t kOffAdj = kOffWh + kWhBytes;
 	static constexpr size_t kOffLb = kOffAdj + kAdjBytes; // look-back partner partials: 256 x (8 + 4) bytes
 	static constexpr size_t kOffDst = kOffLb + (size_t)kBins * 12; // fused mode: per-destination offsets
-	static constexpr size_t kOffMisc = kOffDst + (size_t)kBins * 12;
+	static constexpr size_t kOffMisc = kOffDst + (size_t)kBins * 16;
 	static constexpr size_t kBytes = kOffMisc + 96;
 };
 
 enum { RANK_TICKET = 0, RANK_BALLOT = 1 };
 
-template <int ES, int PL, int DM, typename OffT, int RANK, class Cfg>
+template <int ES, int PL, int DM, bool FUSED, typename OffT, int RANK, class Cfg>
 __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel(const ScatterParams p) {
 	using R = typename Rec<ES>::type;
 	using P = typename Payload<PL>::type;
@@ -220,12 +222,13 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 	R *s_stage = reinterpret_cast<R *>(smem);
 	P *s_stage_pl = reinterpret_cast<P *>(smem + SM::kRecBytes);
 	R *s_rec = reinterpret_cast<R *>(smem + SM::kOffSorted);
-	P *s_pl = reinterpret_cast<P *>(smem + SM::kOffSorted + SM::kRecBytes);
+	P *s_pl = reinterpret_cast<P *>(smem + SM::kOffSorted + SM::kRecBytes + SM::kSortedSlack);
 	uint32_t *s_wh = reinterpret_cast<uint32_t *>(smem + SM::kOffWh);
 	OffT *s_gadj = reinterpret_cast<OffT *>(smem + SM::kOffAdj);
 	unsigned long long *s_gptr = reinterpret_cast<unsigned long long *>(smem + SM::kOffAdj); // fused mode view
 	unsigned long long *s_dexcl = reinterpret_cast<unsigned long long *>(smem + SM::kOffDst); // fused mode
 	uint32_t *s_dstart = reinterpret_cast<uint32_t *>(smem + SM::kOffDst + (size_t)kBins * 8);
+	uint32_t *s_dcount = reinterpret_cast<uint32_t *>(smem + SM::kOffDst + (size_t)kBins * 12);
 	OffT *s_lbsum = reinterpret_cast<OffT *>(smem + SM::kOffLb);
 	uint32_t *s_lbst = reinterpret_cast<uint32_t *>(smem + SM::kOffLb + (size_t)kBins * 8);
 	uint32_t *s_misc = reinterpret_cast<uint32_t *>(smem + SM::kOffMisc);
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 	OffT *status = static_cast<OffT *>(p.status);
 	const R pad = make_pad<ES>(p.pad_rec);
 	const uint32_t full_tiles = (uint32_t)(p.n / TILE); // tiles [0, full_tiles) are complete
-	const uint32_t my_owner = (p.dest_base != nullptr && tid < kBins) ? p.owner[tid] : 0u;
+	const uint32_t my_owner = (FUSED && tid < kBins) ? p.owner[tid] : 0u;
 
 	auto prefetch = [&](uint32_t t) { // one thread
 		const size_t base = (size_t)t * TILE;
@@ -307,8 +310,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 			uint4 *z = reinterpret_cast<uint4 *>(wh);
 			z[lane] = make_uint4(0, 0, 0, 0);
 			z[lane + 32] = make_uint4(0, 0, 0, 0);
-			if (p.dest_base != nullptr && tid < kBins)
-				s_dexcl[tid] = 0;
+
 		}
 		if (staged) {
 			mbar_wait(s_bar, phase);
@@ -373,17 +375,25 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		RSX_T(2);
 
 		// ---- 3a. digit threads: warp prefixes, tile scan, publish aggregate ----
+		constexpr bool fusedm = FUSED;
 		uint32_t tcount = 0, tstart = 0;
 		if (tid < kBins) {
 			uint32_t c[WARPS];
+			if constexpr (FUSED) {
+				// reset the per-destination accumulators: every reader of the previous tile's values
+				// is past barrier (A), every adder of this tile is behind the scan's bar.sync below
+				s_dexcl[tid] = 0;
+				s_dcount[tid] = 0;
+			}
 #pragma unroll
 			for (int w = 0; w < WARPS; ++w)
 				c[w] = s_wh[w * kBins + tid];
 #pragma unroll
 			for (int w = 0; w < WARPS; ++w)
 				tcount += c[w];
-			// tail padding sorts last (digit 255, after every real record): not part of the aggregate
-			const uint32_t agg = (!full && tid == kBins - 1) ? tcount - ((uint32_t)TILE - valid) : tcount;
+			// tail padding sorts last (after every real record of the last used digit): not part of the aggregate
+			const uint32_t pad_digit = DM == DIGIT_SPLIT ? p.nsplit : (uint32_t)kBins - 1;
+			const uint32_t agg = (!full && tid == pad_digit) ? tcount - ((uint32_t)TILE - valid) : tcount;
 			st_status(&status[(size_t)tile * kBins + tid], (OffT)((tile == 0 ? SB::kPfx : SB::kAgg) | (OffT)agg));
 			// exclusive scan of tcount over the 256 digit threads (8 warps)
 			uint32_t x = tcount;
@@ -417,18 +427,21 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 			tcount = agg;
 		}
 		RSX_T(3);
-		__syncthreads(); // (C)
-		RSX_T(4);
 
 		// ---- 4. records / payloads to their tile-sorted slot ----
+		auto place_records = [&]() {
 #pragma unroll
-		for (int i = 0; i < ITEMS; ++i) {
-			const R r = s_stage[t0 + i * 32];
-			const uint32_t pos = wh[tile_digit<ES, DM>(p, r, dd)] + rank[i];
-			s_rec[pos] = r;
-			if constexpr (PL != 0)
-				s_pl[pos] = synth ? (P)(base + t0 + i * 32) : s_stage_pl[t0 + i * 32];
-		}
+			for (int i = 0; i < ITEMS; ++i) {
+				const R r = s_stage[t0 + i * 32];
+				const uint32_t pos = wh[tile_digit<ES, DM>(p, r, dd)] + rank[i];
+				s_rec[pos] = r;
+				if constexpr (PL != 0)
+					s_pl[pos] = synth ? (P)(base + t0 + i * 32) : s_stage_pl[t0 + i * 32];
+			}
+		};
+		__syncthreads(); // (C)
+		RSX_T(4);
+		place_records();
 		RSX_T(5);
 
 		// ---- 3b. decoupled look-back, one chain per digit.  The first round is split over two
@@ -508,15 +521,32 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 				}
 				if (tile != 0)
 					st_status(&status[(size_t)tile * kBins + dgt], (OffT)(SB::kPfx | (excl + (OffT)tcount)));
-				if (p.dest_base != nullptr) {
-					// per-destination running offset = sum of its buckets' exclusive prefixes; the
-					// destination's records are one contiguous range of the tile-sorted buffer
+				if (fusedm) {
+					// Per destination D (a contiguous range of digits, hence one contiguous run of the
+					// sorted buffer): remote element offset = sum of its digits' exclusive prefixes,
+					// records = sum of its digits' counts, run start = its first digit's tstart.
+					// Lanes of one destination are contiguous in a warp: segmented warp reduction,
+					// then one shared atomic per (warp, destination) -- 64-bit shared atomics are CAS
+					// loops and 128 digit threads hammering one address cost more than the whole pass.
 					const uint32_t D = my_owner;
-					atomicAdd(&s_dexcl[D], (unsigned long long)excl);
+					const uint32_t grp = __match_any_sync(FULL, D);
+					unsigned long long ex = (unsigned long long)excl;
+					uint32_t cnt = tcount;
+#pragma unroll
+					for (int o = 1; o < 32; o <<= 1) {
+						const unsigned long long ex2 = __shfl_down_sync(FULL, ex, o);
+						const uint32_t cnt2 = __shfl_down_sync(FULL, cnt, o);
+						if (lane + o < 32 && ((grp >> (lane + o)) & 1u)) {
+							ex += ex2;
+							cnt += cnt2;
+						}
+					}
+					if (lane == (uint32_t)__ffs(grp) - 1) {
+						atomicAdd(&s_dexcl[D], ex);
+						atomicAdd(&s_dcount[D], cnt);
+					}
 					if (dgt == 0 || p.owner[dgt - 1] != D)
 						s_dstart[D] = tstart;
-					asm volatile("bar.sync 1, 256;" ::: "memory");
-					s_gptr[dgt] = p.dest_base[D] + (s_dexcl[D] - (unsigned long long)s_dstart[D]) * ES;
 				} else {
 					s_gadj[dgt] = (OffT)p.offs[dgt] + excl - (OffT)tstart;
 				}
@@ -532,11 +562,42 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		RSX_T(7);
 
 		// ---- 5. coalesced per-bucket stores ----
-		if (p.dest_base != nullptr) { // straight into the owner's buffer (peer memory over NVLink)
-			for (uint32_t s = tid; s < valid; s += THREADS) {
-				const R r = s_rec[s];
-				R *dst = reinterpret_cast<R *>(s_gptr[tile_digit<ES, DM>(p, r, dd)]) + s;
-				*dst = r;
+		if (fusedm) {
+			// Straight into the owners' buffers (peer memory over NVLink).  Per destination one
+			// contiguous run; its body goes out as 16-byte vector stores aligned to the REMOTE address
+			// (708 vs 480 GB/s for 4-byte stores, tools/peer_bw.py).  The shared-memory side is then
+			// misaligned by a per-run constant: two aligned 16-byte loads + a funnel shift.
+			constexpr uint32_t G = ES >= 16 ? 1u : 16u / ES; // records per 16-byte chunk
+			for (uint32_t k = 0; k < p.ndest; ++k) {
+				const uint32_t beg = s_dstart[k], end = beg + s_dcount[k];
+				const unsigned long long r0 = p.dest_base[k] + s_dexcl[k] * ES; // remote byte address of slot `beg`
+				uint32_t a0 = beg + (uint32_t)((G - ((r0 / ES) & (G - 1))) & (G - 1));
+				if (a0 > end)
+					a0 = end;
+				const uint32_t a1 = a0 + (end - a0) / G * G;
+				const uint32_t nhead = a0 - beg, ntail = end - a1;
+				if (tid < nhead + ntail) {
+					const uint32_t sl = tid < nhead ? beg + tid : a1 + (tid - nhead);
+					*reinterpret_cast<R *>(r0 + (unsigned long long)(sl - beg) * ES) = s_rec[sl];
+				}
+				if constexpr (ES < 16) {
+					const uint32_t shb = (a0 & (G - 1)) * ES;          // byte misalignment of the shared side
+					const uint32_t dw = shb >> 2, db = (shb & 3u) * 8u; // whole words + bits inside a word
+					const uint4 *sv = reinterpret_cast<const uint4 *>(s_rec + (a0 - (a0 & (G - 1))));
+					uint4 *rv = reinterpret_cast<uint4 *>(r0 + (unsigned long long)(a0 - beg) * ES);
+					for (uint32_t q = tid; q < (a1 - a0) / G; q += THREADS) {
+						const uint4 v0 = sv[q], v1 = sv[q + 1];
+						const uint32_t w[9] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, 0u};
+						uint4 o;
+						switch (dw) {
+						case 0: o = make_uint4(__funnelshift_r(w[0], w[1], db), __funnelshift_r(w[1], w[2], db), __funnelshift_r(w[2], w[3], db), __funnelshift_r(w[3], w[4], db)); break;
+						case 1: o = make_uint4(__funnelshift_r(w[1], w[2], db), __funnelshift_r(w[2], w[3], db), __funnelshift_r(w[3], w[4], db), __funnelshift_r(w[4], w[5], db)); break;
+						case 2: o = make_uint4(__funnelshift_r(w[2], w[3], db), __funnelshift_r(w[3], w[4], db), __funnelshift_r(w[4], w[5], db), __funnelshift_r(w[5], w[6], db)); break;
+						default: o = make_uint4(__funnelshift_r(w[3], w[4], db), __funnelshift_r(w[4], w[5], db), __funnelshift_r(w[5], w[6], db), __funnelshift_r(w[6], w[7], db)); break;
+						}
+						rv[q] = o;
+					}
+				}
 			}
 		} else if (full) {
 #pragma unroll
@@ -572,10 +633,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 #endif
 }
 
-template <int ES, int PL, int DM, typename OffT, int RANK, class Cfg>
+template <int ES, int PL, int DM, bool FUSED, typename OffT, int RANK, class Cfg>
 cudaError_t launch_scatter_c(const ScatterParams &sp, int num_sms, cudaStream_t st) {
 	using SM = ScatterSmem<ES, PL, Cfg>;
-	auto kern = scatter_kernel<ES, PL, DM, OffT, RANK, Cfg>;
+	auto kern = scatter_kernel<ES, PL, DM, FUSED, OffT, RANK, Cfg>;
 	static int occ_cache[64] = {}; // per device
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -600,25 +661,36 @@ cudaError_t launch_scatter_c(const ScatterParams &sp, int num_sms, cudaStream_t 
 	return cudaGetLastError();
 }
 
-template <int ES, int PL, int DM, typename OffT, int RANK>
+template <int ES, int PL, int DM, bool FUSED, typename OffT, int RANK>
 cudaError_t launch_scatter_r(const ScatterParams &sp, int num_sms, cudaStream_t st) {
-	if constexpr ((ES == 4 || ES == 8) && PL == 0 && DM == DIGIT_PLAIN && RANK == RANK_TICKET && sizeof(OffT) == 4) {
+	if constexpr ((ES == 4 || ES == 8) && PL == 0 && DM == DIGIT_PLAIN && !FUSED && RANK == RANK_TICKET && sizeof(OffT) == 4) {
 		switch (scatter_variant()) {
-		case 1: return launch_scatter_c<ES, PL, DM, OffT, RANK, ScatterCfgV<ES, PL, 1>>(sp, num_sms, st);
-		case 2: return launch_scatter_c<ES, PL, DM, OffT, RANK, ScatterCfgV<ES, PL, 2>>(sp, num_sms, st);
-		case 3: return launch_scatter_c<ES, PL, DM, OffT, RANK, ScatterCfgV<ES, PL, 3>>(sp, num_sms, st);
-		case 4: return launch_scatter_c<ES, PL, DM, OffT, RANK, ScatterCfgV<ES, PL, 4>>(sp, num_sms, st);
-		case 5: return launch_scatter_c<ES, PL, DM, OffT, RANK, ScatterCfgV<ES, PL, 5>>(sp, num_sms, st);
+		case 1: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 1>>(sp, num_sms, st);
+		case 2: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 2>>(sp, num_sms, st);
+		case 3: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 3>>(sp, num_sms, st);
+		case 4: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 4>>(sp, num_sms, st);
+		case 5: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 5>>(sp, num_sms, st);
 		default: break;
 		}
 	}
-	return launch_scatter_c<ES, PL, DM, OffT, RANK, ScatterCfg<ES, PL>>(sp, num_sms, st);
+	return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfg<ES, PL>>(sp, num_sms, st);
 }
 
 template <int ES, int PL, int DM, typename OffT>
 cudaError_t launch_scatter_t(const ScatterParams &sp, int num_sms, cudaStream_t st) {
-	return rank_mode() == RANK_TICKET ? launch_scatter_r<ES, PL, DM, OffT, RANK_TICKET>(sp, num_sms, st)
-	                                  : launch_scatter_r<ES, PL, DM, OffT, RANK_BALLOT>(sp, num_sms, st);
+	const bool ticket = rank_mode() == RANK_TICKET;
+	if (sp.dest_base != nullptr) { // fused partition + exchange (records only)
+		if constexpr (PL == 0)
+			return ticket ? launch_scatter_r<ES, PL, DM, true, OffT, RANK_TICKET>(sp, num_sms, st)
+			              : launch_scatter_r<ES, PL, DM, true, OffT, RANK_BALLOT>(sp, num_sms, st);
+		else
+			return cudaErrorInvalidValue;
+	}
+	if constexpr (DM == DIGIT_SPLIT)
+		return cudaErrorInvalidValue; // key-range routing exists in fused form only
+	else
+		return ticket ? launch_scatter_r<ES, PL, DM, false, OffT, RANK_TICKET>(sp, num_sms, st)
+		              : launch_scatter_r<ES, PL, DM, false, OffT, RANK_BALLOT>(sp, num_sms, st);
 }
 
 template <int ES, int PL>
