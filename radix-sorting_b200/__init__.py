@@ -24,7 +24,7 @@ from dataclasses import dataclass
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librsx.so")
+LIB_PATH = os.environ.get("RSX_LIB", os.path.join(HERE, "librsx.so"))  # RSX_LIB: A/B another build
 
 KDF_UNSIGNED, KDF_SIGNED, KDF_FLOAT = 0, 1, 2
 FLAG_INVERT = 1
@@ -88,12 +88,14 @@ def _lib() -> C.CDLL:
     L.rsx_histogram.argtypes = [vp, sz, LP, u64p, u64p, RP, vp]
     L.rsx_scatter_pass.restype = C.c_int
     L.rsx_scatter_pass.argtypes = [vp, vp, vp, vp, C.c_int, sz, LP, C.c_int, vp]
-    L.rsx_scatter_pass_to.restype = C.c_int
-    L.rsx_scatter_pass_to.argtypes = [vp, sz, LP, C.c_int, C.POINTER(C.c_uint8), u64p, C.c_int, vp]
-    L.rsx_split_counts.restype = C.c_int
-    L.rsx_split_counts.argtypes = [vp, sz, LP, u64p, C.c_int, u64p, vp]
-    L.rsx_split_pass_to.restype = C.c_int
-    L.rsx_split_pass_to.argtypes = [vp, sz, LP, u64p, C.c_int, u64p, vp]
+    if hasattr(L, "rsx_scatter_pass_to"):
+        L.rsx_scatter_pass_to.restype = C.c_int
+        L.rsx_scatter_pass_to.argtypes = [vp, sz, LP, C.c_int, C.POINTER(C.c_uint8), u64p, C.c_int, vp]
+    if hasattr(L, "rsx_split_counts"):  # absent only in older builds loaded through RSX_LIB for A/B runs
+        L.rsx_split_counts.restype = C.c_int
+        L.rsx_split_counts.argtypes = [vp, sz, LP, u64p, C.c_int, u64p, vp]
+        L.rsx_split_pass_to.restype = C.c_int
+        L.rsx_split_pass_to.argtypes = [vp, sz, LP, u64p, C.c_int, u64p, vp]
     L.rsx_workspace_bytes.restype = sz
     L.rsx_workspace_bytes.argtypes = [sz, LP, C.c_int]
     L.rsx_reserve.restype = C.c_int

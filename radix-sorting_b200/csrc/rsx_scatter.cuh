@@ -195,7 +195,7 @@ template <int ES, int PL, class Cfg> struct ScatterSmem {
 	static constexpr size_t kAdjBytes = (size_t)kBins * 8;
 	// layout: [stage rec | stage pl | sorted rec | sorted pl | warp counters | gadj | misc]
 	static constexpr size_t kOffSorted = kStageBytes;
-	static constexpr size_t kSortedSlack = 32; // fused mode reads one 16-byte vector past a run's last chunk
+	static constexpr size_t kSortedSlack = 0; // fused mode may read one 16-byte vector past the sorted buffer: that is the counter area, harmless
 	static constexpr size_t kOffWh = kOffSorted + kRecBytes + kSortedSlack + kPlBytes;
 	static constexpr size_t kOffAdj = kOffWh + kWhBytes;
 	static constexpr size_t kOffLb = kOffAdj + kAdjBytes; // look-back partner partials: 256 x (8 + 4) bytes
@@ -428,20 +428,18 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		}
 		RSX_T(3);
 
-		// ---- 4. records / payloads to their tile-sorted slot ----
-		auto place_records = [&]() {
-#pragma unroll
-			for (int i = 0; i < ITEMS; ++i) {
-				const R r = s_stage[t0 + i * 32];
-				const uint32_t pos = wh[tile_digit<ES, DM>(p, r, dd)] + rank[i];
-				s_rec[pos] = r;
-				if constexpr (PL != 0)
-					s_pl[pos] = synth ? (P)(base + t0 + i * 32) : s_stage_pl[t0 + i * 32];
-			}
-		};
 		__syncthreads(); // (C)
 		RSX_T(4);
-		place_records();
+
+		// ---- 4. records / payloads to their tile-sorted slot ----
+#pragma unroll
+		for (int i = 0; i < ITEMS; ++i) { // fully unrolled on purpose: partial unrolling costs 10 %
+			const R r = s_stage[t0 + i * 32];
+			const uint32_t pos = wh[tile_digit<ES, DM>(p, r, dd)] + rank[i];
+			s_rec[pos] = r;
+			if constexpr (PL != 0)
+				s_pl[pos] = synth ? (P)(base + t0 + i * 32) : s_stage_pl[t0 + i * 32];
+		}
 		RSX_T(5);
 
 		// ---- 3b. decoupled look-back, one chain per digit.  The first round is split over two
@@ -600,7 +598,14 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 				}
 			}
 		} else if (full) {
-#pragma unroll
+			// partial unroll: stores start flowing after a few loads instead of after all of them
+			// (1 B u32: 2.87 ms per pass vs 2.96 fully unrolled)
+#ifdef RSX_WRITE_UNROLL
+			constexpr int kWriteUnroll = RSX_WRITE_UNROLL;
+#else
+			constexpr int kWriteUnroll = (ITEMS % 5 == 0) ? 5 : 4;
+#endif
+#pragma unroll(kWriteUnroll)
 			for (int i = 0; i < ITEMS; ++i) {
 				const uint32_t s = tid + i * THREADS;
 				const R r = s_rec[s];
