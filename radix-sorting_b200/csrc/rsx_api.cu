@@ -20,6 +20,7 @@ namespace rsx {
 
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<int> g_force_wide{0};
+static std::atomic<int> g_small_path{1};
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 namespace {
@@ -515,6 +516,10 @@ int rsx_set_option(const char *name, long value) {
 		g_variant.store((int)value);
 		return RSX_OK;
 	}
+	if (name && strcmp(name, "small_path") == 0) { // 0: always use the multi-kernel path (tests)
+		g_small_path.store(value ? 1 : 0);
+		return RSX_OK;
+	}
 	if (name && strcmp(name, "force_wide") == 0) { // tests: run the n >= 2^30 (64-bit offset) kernels at small n
 		g_force_wide.store(value ? 1 : 0);
 		return RSX_OK;
@@ -573,6 +578,24 @@ void rsx_release(void) {
 static int sort_device(void *src, void *aux, size_t n, const rsx_layout *layout, const KeyDesc &kd,
                        void **result, rsx_report *rep, cudaStream_t st, int dev, bool staged) {
 	const unsigned long long l0 = g_launches.load();
+	if (g_small_path.load(std::memory_order_relaxed) && n <= small_sort_capacity(layout->record_bytes, false)) {
+		// one CTA, one launch (rsx_small.cu)
+		Lease L;
+		int r = acquire(L, dev, sizeof(WsHead) + 256);
+		if (r)
+			return r;
+		WsHead *ws = static_cast<WsHead *>(L.ptr);
+		prof_mark(st, true);
+		CU(launch_small_sort(src, src, aux, nullptr, 0, n, layout->record_bytes, kd, &ws->ctl, st));
+		prof_mark(st);
+		rsx_report local;
+		if (!rep)
+			rep = &local;
+		if ((r = read_ctl(static_cast<unsigned char *>(L.ptr), L.pinned, st, l0, rep, staged)))
+			return r;
+		*result = rep->result_in_aux ? aux : src;
+		return RSX_OK;
+	}
 	Plan P;
 	make_plan(P, n, layout, kd, 0);
 	Lease L;
@@ -659,6 +682,23 @@ int rsx_sort(void *src, void *aux, size_t n, const rsx_layout *layout, void **re
 static int rank_device(const void *src, void *ib, size_t n, const rsx_layout *layout, const KeyDesc &kd,
                        int idx_bytes, void **result, rsx_report *rep, cudaStream_t st, int dev, bool staged) {
 	const unsigned long long l0 = g_launches.load();
+	if (g_small_path.load(std::memory_order_relaxed) && n <= small_sort_capacity(layout->record_bytes, true)) {
+		Lease L;
+		int r = acquire(L, dev, sizeof(WsHead) + 256);
+		if (r)
+			return r;
+		WsHead *wsh = static_cast<WsHead *>(L.ptr);
+		prof_mark(st, true);
+		CU(launch_small_sort(src, nullptr, nullptr, ib, idx_bytes, n, layout->record_bytes, kd, &wsh->ctl, st));
+		prof_mark(st);
+		rsx_report local;
+		if (!rep)
+			rep = &local;
+		if ((r = read_ctl(static_cast<unsigned char *>(L.ptr), L.pinned, st, l0, rep, staged)))
+			return r;
+		*result = static_cast<unsigned char *>(ib) + (rep->result_in_aux ? n * (size_t)idx_bytes : 0);
+		return RSX_OK;
+	}
 	Plan P;
 	make_plan(P, n, layout, kd, idx_bytes);
 	Lease L;

@@ -91,6 +91,11 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
 
 PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes);
 
+// single-CTA path for inputs that fit one CTA's shared memory (rsx_small.cu)
+size_t small_sort_capacity(uint32_t record_bytes, bool ranksort);
+cudaError_t launch_small_sort(const void *src, void *out_even, void *out_odd, void *index_buffer, int idx_bytes,
+                              size_t n, uint32_t record_bytes, const KeyDesc &kd, Ctl *ctl, cudaStream_t st);
+
 // rank-sort helpers
 cudaError_t launch_iota_if_early(void *index_buffer, int idx_bytes, size_t n, const Ctl *ctl,
                                  cudaStream_t st);

@@ -62,10 +62,19 @@ def gpu_rank(rsx, torch, tname, data, idx_dtype=np.uint32, descending=False):
     return ranks, rep, ib.cpu().numpy().view(idx_dtype)
 
 
+@pytest.fixture(params=["single-cta", "multi-kernel"])
+def both_paths(request, rsx):
+    """Inputs that fit one CTA take the single-launch kernel (rsx_small.cu); run the same case
+    through the multi-kernel path too, so that both stay pinned on the small goldens."""
+    rsx.lib().rsx_set_option(b"small_path", 1 if request.param == "single-cta" else 0)
+    yield request.param
+    rsx.lib().rsx_set_option(b"small_path", 1)
+
+
 # ---- golden digests of the unmodified reference --------------------------------------------------
 
 @pytest.mark.parametrize("c", GOLDEN_CASES, ids=case_id)
-def test_sort_matches_reference_golden(rsx, torch, oracle, c):
+def test_sort_matches_reference_golden(rsx, torch, oracle, both_paths, c):
     t = TYPES[c[0]]
     data = make_input(c[0], c[1], 1234, c[2], c[3], c[4])
     out, rep, in_aux = gpu_sort(rsx, torch, c[0], data)
@@ -83,7 +92,7 @@ def test_sort_matches_reference_golden(rsx, torch, oracle, c):
 
 
 @pytest.mark.parametrize("c", [c for c in GOLDEN_CASES if c[1] in (2, 257, 1000, 5000, 70001)], ids=case_id)
-def test_rank_matches_oracle(rsx, torch, oracle, c):
+def test_rank_matches_oracle(rsx, torch, oracle, both_paths, c):
     t = TYPES[c[0]]
     data = make_input(c[0], c[1], 1234, c[2], c[3], c[4])
     for idt in (np.uint32, np.uint64):
@@ -113,7 +122,7 @@ def _records(layout, keys):
 
 
 @pytest.mark.parametrize("v", VEC["value_sorts"], ids=lambda v: v["name"][:40])
-def test_reference_value_vectors(rsx, torch, v):
+def test_reference_value_vectors(rsx, torch, both_paths, v):
     rb, ko, kb, kind, flags = v["layout"]
     raw = _records(v["layout"], v["keys"])
     src = torch.from_numpy(raw.reshape(-1).copy()).cuda()
@@ -127,7 +136,7 @@ def test_reference_value_vectors(rsx, torch, v):
     assert (res.data_ptr() == aux.data_ptr()) == bool(v["result_in_aux"])
 
 
-def test_reference_float_vector(rsx, torch):
+def test_reference_float_vector(rsx, torch, both_paths):
     v = VEC["float_sort"]
     data = np.array([int(x, 16) for x in v["input_bits"]], dtype=np.uint32).view(np.float32)
     src = torch.from_numpy(data.copy()).cuda()
@@ -138,7 +147,7 @@ def test_reference_float_vector(rsx, torch):
 
 
 @pytest.mark.parametrize("v", VEC["rank_sorts"], ids=lambda v: v["name"][:40])
-def test_reference_rank_vectors(rsx, torch, v):
+def test_reference_rank_vectors(rsx, torch, both_paths, v):
     rb, ko, kb, kind, flags = v["layout"]
     raw = _records(v["layout"], v["keys"])
     n = len(v["keys"])
@@ -444,3 +453,18 @@ def test_multipass_composite_key_like_listing5(rsx, torch, oracle):
     hi = rsx.radix_sort(lo, other, None, rsx.KeyFunc(rsx.KDF_UNSIGNED, False, 16, 4, 4))
     want, _, _ = oracle.radix_sort(data, TYPES["rec16_u64"].layout())
     assert hi.cpu().numpy().tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("tname", ["u8", "u32", "i64", "f64", "rec16_u8", "rec16_u64"])
+def test_single_cta_capacity_boundary(rsx, torch, oracle, tname):
+    """n at, just below and just above the single-CTA kernel's capacity (value and rank sorts)."""
+    t = TYPES[tname]
+    for cap in {min((65536 - 16) // t.record_bytes, 16384), min((65536 - 16) // (t.record_bytes + 4), 16384)}:
+        for n in (cap - 1, cap, cap + 1):
+            data = make_input(tname, n, 5, "and2")
+            out, rep, _ = gpu_sort(rsx, torch, tname, data)
+            want, orep, _ = oracle.radix_sort(data, t.layout())
+            assert out.tobytes() == want.tobytes() and rep.result_in_aux == orep.result_in_aux, (tname, n)
+            ranks, rrep, _ = gpu_rank(rsx, torch, tname, data, np.uint32)
+            wr, worep, _ = oracle.radix_sort_rank(data, t.layout(), np.uint32)
+            assert np.array_equal(ranks, wr) and rrep.result_in_aux == worep.result_in_aux, (tname, n)
