@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 			const uint32_t hot = s_misc[9];
 			uint32_t hotcnt = 0;
 #pragma unroll
-			for (int i = 0; i < ITEMS; ++i) {
+			for (int i = 0; i < ITEMS; ++i) { // fully unrolled on purpose (partial: +8 %)
 				const uint32_t d = tile_digit<ES, DM>(p, s_stage[t0 + i * 32], dd);
 				const bool is_hot = d == hot;
 				const uint32_t m = __ballot_sync(FULL, is_hot);
@@ -610,10 +610,15 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 				const uint32_t s = tid + i * THREADS;
 				const R r = s_rec[s];
 				const OffT g = s_gadj[tile_digit<ES, DM>(p, r, dd)] + (OffT)s;
-				if (write_rec)
-					out[g] = r;
-				if constexpr (PL != 0)
-					pout[g] = s_pl[s];
+				if constexpr (ES + PL <= 4) { // streaming (evict-first) stores: 1.4 % on 4-byte keys, neutral or worse on wider records
+					if (write_rec)
+						__stcs(out + g, r);
+				} else {
+					if (write_rec)
+						out[g] = r;
+					if constexpr (PL != 0)
+						pout[g] = s_pl[s];
+				}
 			}
 		} else {
 			for (uint32_t s = tid; s < valid; s += THREADS) {
