@@ -294,9 +294,17 @@ def main():
     alg_bytes_pass = 2 * n * kb  # read n records + write n records (2K per key per pass)
     achieved = alg_bytes_pass / (avg_pass * 1e-3) / 1e9
     alg_bytes_sort = n * kb * (1 + 2 * passes)
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes of this kernel from the committed ncu --set full capture, scaled to this n
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["scatter_kernel"]["u32" if kb == 4 else "u64"]
+        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * n / tj["keys"]
+        traffic_src = "dram__bytes_read.sum + dram__bytes_write.sum of one launch at 256 M keys (profiles/r1_final_ncu.md), scaled by n"
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": "scatter_kernel (K3, one launch per live column)",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "traffic_source": traffic_src,
         "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_pass, "ms_per_launch": avg_pass,
         "launches_timed": len(pass_ms),
         "histogram_kernel": {"ms": sum(hist_ms) / len(hist_ms), "alg_bytes": n * kb,
