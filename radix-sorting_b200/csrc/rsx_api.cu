@@ -629,6 +629,12 @@ int rsx_sort(void *src, void *aux, size_t n, const rsx_layout *layout, void **re
 		return r;
 	if (!result || (n && (!src || !aux)))
 		return RSX_ERR_INVALID;
+	if (n >= 2) { // src and aux are __restrict__ in the reference (radix_sort.hpp:32): overlapping buffers are a bug
+		const unsigned char *a = static_cast<const unsigned char *>(src), *b = static_cast<const unsigned char *>(aux);
+		const size_t bytes = n * layout->record_bytes;
+		if (a < b + bytes && b < a + bytes)
+			return RSX_ERR_INVALID;
+	}
 	if (n < 2) { // radix_sort.hpp:100-101
 		*result = src;
 		trivial_report(rep);

@@ -468,3 +468,64 @@ def test_single_cta_capacity_boundary(rsx, torch, oracle, tname):
             ranks, rrep, _ = gpu_rank(rsx, torch, tname, data, np.uint32)
             wr, worep, _ = oracle.radix_sort_rank(data, t.layout(), np.uint32)
             assert np.array_equal(ranks, wr) and rrep.result_in_aux == worep.result_in_aux, (tname, n)
+
+
+# ---- boundary behaviour: threads, managed memory, overlapping buffers ------------------------------------
+
+def test_concurrent_host_threads(rsx, torch, oracle):
+    """safe to call from several host threads (per-call workspace, no global mutable state)."""
+    import threading
+    results, errors = {}, []
+
+    def work(k):
+        try:
+            t = TYPES["u32" if k % 2 == 0 else "u64"]
+            data = make_input(t.name, 400000 + 1000 * k, 100 + k)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for _ in range(5):
+                    out, rep, _ = gpu_sort(rsx, torch, t.name, data)
+            want, _, _ = oracle.radix_sort(data, t.layout())
+            results[k] = out.tobytes() == want.tobytes()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    assert all(results.get(k) for k in range(4)), results
+
+
+def test_managed_memory_is_sorted_in_place(rsx, torch, oracle):
+    """cudaMallocManaged buffers are treated like device memory (no staging)."""
+    import ctypes as C
+    cudart = C.CDLL("libcudart.so.12")
+    n = 123457
+    data = make_input("i32", n, 8)
+    src, aux = C.c_void_p(), C.c_void_p()
+    assert cudart.cudaMallocManaged(C.byref(src), C.c_size_t(4 * n), C.c_uint(1)) == 0
+    assert cudart.cudaMallocManaged(C.byref(aux), C.c_size_t(4 * n), C.c_uint(1)) == 0
+    try:
+        C.memmove(src, data.ctypes.data, 4 * n)
+        L = rsx.RsxLayout(4, 0, 4, rsx.KDF_SIGNED, 0)
+        res, rep = C.c_void_p(), rsx.RsxReport()
+        assert rsx.lib().rsx_sort(src, aux, n, C.byref(L), C.byref(res), C.byref(rep), None) == 0
+        assert rep.staged == 0
+        torch.cuda.synchronize()
+        out = np.empty(n, dtype=np.int32)
+        C.memmove(out.ctypes.data, res, 4 * n)
+        assert np.array_equal(out, np.sort(data, kind="stable"))
+    finally:
+        cudart.cudaFree(src)
+        cudart.cudaFree(aux)
+
+
+def test_overlapping_buffers_are_rejected(rsx, torch):
+    import ctypes as C
+    buf = torch.zeros(1000, dtype=torch.int32, device="cuda")
+    L = rsx.RsxLayout(4, 0, 4, 0, 0)
+    res = C.c_void_p()
+    st = rsx.lib().rsx_sort(buf.data_ptr(), buf.data_ptr() + 400, 600, C.byref(L), C.byref(res), None, None)
+    assert st == rsx.RSX_ERR_INVALID
