@@ -42,6 +42,8 @@ WORKLOADS = {
     "2B-u64-uniform": ("u64", 2_000_000_000, "uniform", _M64, 0, 8),       # per-GPU shard of configs[4]
     "2B-u64-zipf": ("u64", 2_000_000_000, "zipf", _M64, 0, 4),             # configs[4], skewed: P(v) ~ 1/v, v < 2^32
     "1B-u32-zipf": ("u32", 1_000_000_000, "zipf", _M64, 0, 4),
+    "8B-u64-uniform": ("u64", 8_000_000_000, "uniform", _M64, 0, 8),       # strong-scaling base: 8 B keys on ONE GPU
+    "4B-u64-uniform": ("u64", 4_000_000_000, "uniform", _M64, 0, 8),
 }
 CPU_SAMPLE_KEYS = {4: 256_000_000, 8: 96_000_000}  # bounded CPU sample, ~10-30 s of single-core work
 
@@ -242,19 +244,32 @@ def main():
         dist.destroy_process_group()
         return
 
-    pristine = torch.empty(n, dtype=tdt, device=dev)
-    rsx.fill_keys(pristine, seed=2 + rank, dist=dname, mask=mask, orv=orv)
-    src = torch.empty_like(pristine)
-    aux = torch.empty_like(pristine)
+    # three full-size buffers (pristine, src, aux) do not fit for the 8 B-key strong-scaling base:
+    # there the input is regenerated in place before every step instead of copied back
+    regen = 3 * n * kb > 0.8 * torch.cuda.get_device_properties(dev).total_memory
+    src = torch.empty(n, dtype=tdt, device=dev)
+    aux = torch.empty_like(src)
+    if regen:
+        pristine = None
+
+        def restore():
+            rsx.fill_keys(src, seed=2 + rank, dist=dname, mask=mask, orv=orv)
+    else:
+        pristine = torch.empty_like(src)
+        rsx.fill_keys(pristine, seed=2 + rank, dist=dname, mask=mask, orv=orv)
+
+        def restore():
+            src.copy_(pristine)
+    restore()
     rsx.reserve(rsx.workspace_bytes(n, kf.layout(kb)))
     rsx.set_profile(True)
     rsx.lib().rsx_set_option(b"rank_mode", args.rank_mode)
     rsx.lib().rsx_set_option(b"scatter_variant", args.variant)
     rank_mode = {0: "ticket", 1: "ballot"}[rsx.lib().rsx_set_option(b"query_rank_mode", 0)]
-    d0, s0, x0 = rsx.verify(pristine, kf)
+    d0, s0, x0 = rsx.verify(src, kf)
 
     def step():
-        src.copy_(pristine)  # restore: outside the events; also evicts L2 (4-8 GB >> 126 MB)
+        restore()  # outside the events; also evicts L2 (4-64 GB >> 126 MB)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         rep = rsx.RsxReport()
         e0.record()
@@ -317,7 +332,7 @@ def main():
 
     # ---- e2e: the same sort through the C ABI with HOST buffers (H2D + sort + D2H timed) ----------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not regen:
         del src, aux
         torch.cuda.empty_cache()
         h_src = torch.empty(n, dtype=tdt, pin_memory=True)
