@@ -196,7 +196,6 @@ def main():
     ap.add_argument("--no-fused", action="store_true", help="N > 1: NCCL all_to_all instead of fused peer stores")
     ap.add_argument("--rank-mode", type=int, default=-1, help="-1 auto (hardware probe), 0 ticket, 1 ballot")
     ap.add_argument("--variant", type=int, default=0, help="scatter tuning variant (rsx_scatter.cuh)")
-    ap.add_argument("--bulk-store", type=int, default=0, help="0: per-record STG write-out instead of TMA bulk stores (A/B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -266,7 +265,6 @@ def main():
     rsx.set_profile(True)
     rsx.lib().rsx_set_option(b"rank_mode", args.rank_mode)
     rsx.lib().rsx_set_option(b"scatter_variant", args.variant)
-    rsx.lib().rsx_set_option(b"bulk_store", args.bulk_store)
     rank_mode = {0: "ticket", 1: "ballot"}[rsx.lib().rsx_set_option(b"query_rank_mode", 0)]
     d0, s0, x0 = rsx.verify(src, kf)
 
@@ -364,7 +362,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": tname, "data": "synthetic",
         "config": {"workload": args.workload, "keys": n, "key_bytes": kb, "live_passes": passes,
-                   "dist": dname, "rank_mode": rank_mode, "variant": args.variant, "bulk_store": args.bulk_store, "l2": "inputs (n*key_bytes) larger than L2 and restored by a full-size copy before every step",
+                   "dist": dname, "rank_mode": rank_mode, "variant": args.variant, "l2": "inputs (n*key_bytes) larger than L2 and restored by a full-size copy before every step",
                    "timing": "CUDA events around each rsx_sort call on the launch stream, mean of steps",
                    "ms_min": min(times), "ms_max": max(times)},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),

@@ -372,8 +372,6 @@ void trivial_report(rsx_report *rep) {
 
 static std::atomic<int> g_variant{0};
 int scatter_variant() { return g_variant.load(std::memory_order_relaxed); }
-static std::atomic<int> g_bulk_store{0};
-int bulk_store_enabled() { return g_bulk_store.load(std::memory_order_relaxed); }
 
 int rank_mode() {
 	const int o = g_rank_override.load(std::memory_order_relaxed);
@@ -516,10 +514,6 @@ int rsx_set_option(const char *name, long value) {
 		if (value < 0 || value >= kNumVariants)
 			return RSX_ERR_INVALID;
 		g_variant.store((int)value);
-		return RSX_OK;
-	}
-	if (name && strcmp(name, "bulk_store") == 0) { // 0: per-record STG write-out (the pre-TMA-store kernel), for A/B runs
-		g_bulk_store.store(value ? 1 : 0);
 		return RSX_OK;
 	}
 	if (name && strcmp(name, "small_path") == 0) { // 0: always use the multi-kernel path (tests)

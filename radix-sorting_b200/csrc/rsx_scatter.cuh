@@ -6,7 +6,7 @@
 // index is computed in parallel as
 //     dst = column_offset[d]                 (exclusive scan of the global histogram, K2)
 //         + #records with digit d in earlier tiles      (decoupled look-back, one chain per digit)
-//         + #records with digit d earlier in this tile  (warp match ranking + cross-warp prefix)
+//         + #records with digit d earlier in this tile  (stable rank in the warp + cross-warp prefix)
 // which is exactly the value the reference's counter would have had, so the output is
 // bit-identical, including the order of equal keys (stability) and of payloads.
 //
@@ -15,7 +15,9 @@
 //
 // Tile pipeline (persistent CTAs, tiles handed out by an atomic ticket so that a tile's
 // predecessors are always owned by running CTAs -> the look-back cannot deadlock):
-//   1. coalesced warp-striped load of the tile into registers; KDF folded into digit_of()
+//   1. the tile sits in a shared staging buffer, put there by a TMA bulk copy issued while the
+//      previous tile was being stored (plain loads for unaligned input and the partial last tile);
+//      warp-striped ownership; the KDF is folded into digit_of()
 //   2. per warp, per item: stable rank of the record among the warp's records with the same
 //      digit.  Two implementations (template RANK):
 //        RANK_TICKET  rank = atomicAdd(&warp_counter[digit], 1): ONE shared-memory instruction
@@ -172,12 +174,12 @@ template <int ES, int PL, int V> struct ScatterCfgV
 	       ((ES + PL <= 4) ? 20 : (ES + PL <= 8) ? 10 : (ES + PL <= 16) ? 8 : 4), ((ES + PL <= 4) ? 2 : 1), 16, true> {};
 constexpr int kNumVariants = 6;
 // tuning variants exist for plain 4- and 8-byte keys only
-template <> struct ScatterCfgV<4, 0, 1> : CfgT<512, 20, 2, 32, true> {};
+template <> struct ScatterCfgV<4, 0, 1> : CfgT<512, 16, 2, 16, true> {};
 template <> struct ScatterCfgV<4, 0, 2> : CfgT<512, 20, 2, 24, true> {};
 template <> struct ScatterCfgV<4, 0, 3> : CfgT<1024, 16, 1, 16, true> {};
 template <> struct ScatterCfgV<4, 0, 4> : CfgT<512, 24, 1, 16, true> {};
 template <> struct ScatterCfgV<4, 0, 5> : CfgT<512, 32, 1, 16, true> {};
-template <> struct ScatterCfgV<8, 0, 1> : CfgT<1024, 10, 1, 32, true> {};
+template <> struct ScatterCfgV<8, 0, 1> : CfgT<512, 8, 2, 16, true> {};
 template <> struct ScatterCfgV<8, 0, 2> : CfgT<1024, 10, 1, 24, true> {};
 template <> struct ScatterCfgV<8, 0, 3> : CfgT<1024, 8, 1, 16, true> {};
 template <> struct ScatterCfgV<8, 0, 4> : CfgT<512, 12, 1, 16, true> {};
@@ -643,18 +645,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 #endif
 }
 
-} // namespace rsx
-#include "rsx_scatter_bulk.cuh"
-namespace rsx {
-
-int bulk_store_enabled(); // rsx_set_option("bulk_store", 0/1), default 0 (experiment, slower: profiles/r1_variants.md)
-
 template <int ES, int PL, int DM, bool FUSED, typename OffT, int RANK, class Cfg>
 cudaError_t launch_scatter_c(const ScatterParams &sp, int num_sms, cudaStream_t st) {
-	if constexpr (!FUSED) { // single-GPU passes: write-out through the copy engine
-		if (bulk_store_enabled())
-			return launch_scatter_bulk<ES, PL, DM, OffT, RANK, Cfg>(sp, num_sms, st);
-	}
 	using SM = ScatterSmem<ES, PL, Cfg>;
 	auto kern = scatter_kernel<ES, PL, DM, FUSED, OffT, RANK, Cfg>;
 	static int occ_cache[64] = {}; // per device

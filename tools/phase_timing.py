@@ -19,9 +19,6 @@ L = mod.RsxLayout(kb, 0, kb, 0, 0)
 dbg.rsx_set_option(b"scatter_variant", variant)
 res = C.c_void_p(); rep = mod.RsxReport()
 names = ["load/wait stage", "rank (atoms)", "barrier A", "digit phase", "barrier C", "scatter->smem", "look-back", "barrier D", "write-out", "loop top", "lb rounds", "lb polls", "CTAs"]
-if int(os.environ.get("RSX_BULK", "1")):  # the TMA-store kernel orders its phases differently
-    names = ["wait stage -> regs", "count (atoms)", "barrier A", "publish+look-back", "wait_group/barrier C", "place (atoms)", "slot scan + bases", "barrier D", "issue stores", "loop top + wait_group.read", "lb rounds", "lb polls", "CTAs"]
-dbg.rsx_set_option(b"bulk_store", int(os.environ.get("RSX_BULK", "1")))
 for it in range(3):
     src.copy_(pristine)
     out = (C.c_ulonglong * 16)()
