@@ -384,20 +384,28 @@ int rank_mode() {
 }
 
 // ---- launch glue declared in rsx_internal.cuh --------------------------------------------------
+// Tile geometry that sizes the look-back state: the smallest tile any kernel of this footprint may
+// run with (the fused geometry, or a smaller tuning variant), so every kernel uses at most this
+// many status rows.
 PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes) {
 	PassGeometry g{};
 	const int v = scatter_variant();
-#define GEOV(ES, PL, V)                                                                  \
-	if (record_bytes == ES && payload_bytes == PL && v == V) {                           \
-		g.threads = ScatterCfgV<ES, PL, V>::kThreads;                                    \
-		g.items = ScatterCfgV<ES, PL, V>::kItems;                                        \
-		g.smem_bytes = ScatterSmem<ES, PL, ScatterCfgV<ES, PL, V>>::kBytes;              \
-	}
-#define GEO(ES, PL)                                                                      \
-	if (record_bytes == ES && payload_bytes == PL) {                                     \
-		g.threads = ScatterCfg<ES, PL>::kThreads;                                        \
-		g.items = ScatterCfg<ES, PL>::kItems;                                            \
-		g.smem_bytes = ScatterSmem<ES, PL, ScatterCfg<ES, PL>>::kBytes;                  \
+	auto take = [&](uint32_t threads, uint32_t items, size_t smem) {
+		if (g.threads == 0 || threads * items < g.threads * g.items) {
+			g.threads = threads;
+			g.items = items;
+			g.smem_bytes = smem;
+		}
+	};
+#define GEOV(ES, PL, V)                                                                          \
+	if (record_bytes == ES && payload_bytes == PL && v == V)                                     \
+		take(ScatterCfgV<ES, PL, V>::kThreads, ScatterCfgV<ES, PL, V>::kItems,                   \
+		     ScatterSmem<ES, PL, ScatterCfgV<ES, PL, V>, false>::kBytes);
+#define GEO(ES, PL)                                                                              \
+	if (record_bytes == ES && payload_bytes == PL) {                                             \
+		static_assert(FusedCfg<ES, PL>::kThreads * FusedCfg<ES, PL>::kItems <=                   \
+		              ScatterCfg<ES, PL>::kThreads * ScatterCfg<ES, PL>::kItems, "fused tile must be the smallest"); \
+		take(FusedCfg<ES, PL>::kThreads, FusedCfg<ES, PL>::kItems, ScatterSmem<ES, PL, FusedCfg<ES, PL>, true>::kBytes); \
 	}
 	GEO(1, 0) GEO(1, 4) GEO(1, 8) GEO(2, 0) GEO(2, 4) GEO(2, 8) GEO(4, 0) GEO(4, 4) GEO(4, 8)
 	GEO(8, 0) GEO(8, 4) GEO(8, 8) GEO(16, 0) GEO(16, 4) GEO(16, 8)

@@ -168,18 +168,24 @@ template <int T, int I, int MB, int LBK, bool ST> struct CfgT {
 };
 // Defaults from the B200 sweeps recorded in profiles/r1_variants.md: the pass is bound by the
 // shared-memory/LSU data pipe, so the largest tile that still leaves two CTAs per SM (4-byte
-// records) or one fat CTA (wider records) wins.
+// records) or one fat CTA (wider records) wins: 512 x 22 fills 2 x 111.7 KB, 1024 x 11 fills 217 KB.
 template <int ES, int PL, int V> struct ScatterCfgV
+	: CfgT<((ES + PL > 4 && ES + PL <= 8) ? 1024 : 512),
+	       ((ES + PL <= 4) ? 22 : (ES + PL <= 8) ? 11 : (ES + PL <= 16) ? 8 : 4), ((ES + PL <= 4) ? 2 : 1), 16, true> {};
+// The fused partition + exchange passes (multi-GPU) carry a 4 KB destination table in shared
+// memory and keep the geometry they were tuned and measured with.  It is the smallest tile of any
+// default kernel, so it also sizes the look-back state (scatter_geometry()).
+template <int ES, int PL> struct FusedCfg
 	: CfgT<((ES + PL > 4 && ES + PL <= 8) ? 1024 : 512),
 	       ((ES + PL <= 4) ? 20 : (ES + PL <= 8) ? 10 : (ES + PL <= 16) ? 8 : 4), ((ES + PL <= 4) ? 2 : 1), 16, true> {};
 constexpr int kNumVariants = 6;
 // tuning variants exist for plain 4- and 8-byte keys only
-template <> struct ScatterCfgV<4, 0, 1> : CfgT<512, 16, 2, 16, true> {};
+template <> struct ScatterCfgV<4, 0, 1> : CfgT<512, 20, 2, 16, true> {};
 template <> struct ScatterCfgV<4, 0, 2> : CfgT<512, 20, 2, 24, true> {};
 template <> struct ScatterCfgV<4, 0, 3> : CfgT<1024, 16, 1, 16, true> {};
 template <> struct ScatterCfgV<4, 0, 4> : CfgT<512, 24, 1, 16, true> {};
 template <> struct ScatterCfgV<4, 0, 5> : CfgT<512, 32, 1, 16, true> {};
-template <> struct ScatterCfgV<8, 0, 1> : CfgT<512, 8, 2, 16, true> {};
+template <> struct ScatterCfgV<8, 0, 1> : CfgT<1024, 10, 1, 16, true> {};
 template <> struct ScatterCfgV<8, 0, 2> : CfgT<1024, 10, 1, 24, true> {};
 template <> struct ScatterCfgV<8, 0, 3> : CfgT<1024, 8, 1, 16, true> {};
 template <> struct ScatterCfgV<8, 0, 4> : CfgT<512, 12, 1, 16, true> {};
@@ -187,7 +193,7 @@ template <> struct ScatterCfgV<8, 0, 5> : CfgT<512, 16, 1, 16, true> {};
 template <int ES, int PL> using ScatterCfg = ScatterCfgV<ES, PL, 0>;
 int scatter_variant();
 
-template <int ES, int PL, class Cfg> struct ScatterSmem {
+template <int ES, int PL, class Cfg, bool FUSED = true> struct ScatterSmem {
 	static constexpr int kTile = Cfg::kThreads * Cfg::kItems;
 	static constexpr int kWarps = Cfg::kThreads / 32;
 	static constexpr size_t kRecBytes = (size_t)kTile * ES;
@@ -202,7 +208,7 @@ template <int ES, int PL, class Cfg> struct ScatterSmem {
 	static constexpr size_t kOffAdj = kOffWh + kWhBytes;
 	static constexpr size_t kOffLb = kOffAdj + kAdjBytes; // look-back partner partials: 256 x (8 + 4) bytes
 	static constexpr size_t kOffDst = kOffLb + (size_t)kBins * 12; // fused mode: per-destination offsets
-	static constexpr size_t kOffMisc = kOffDst + (size_t)kBins * 16;
+	static constexpr size_t kOffMisc = kOffDst + (FUSED ? (size_t)kBins * 16 : 0); // single-GPU passes have no destination table
 	static constexpr size_t kBytes = kOffMisc + 96;
 };
 
@@ -212,7 +218,7 @@ template <int ES, int PL, int DM, bool FUSED, typename OffT, int RANK, class Cfg
 __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel(const ScatterParams p) {
 	using R = typename Rec<ES>::type;
 	using P = typename Payload<PL>::type;
-	using SM = ScatterSmem<ES, PL, Cfg>;
+	using SM = ScatterSmem<ES, PL, Cfg, FUSED>;
 	using SB = StatusBits<OffT>;
 	constexpr int THREADS = Cfg::kThreads, ITEMS = Cfg::kItems;
 	constexpr int TILE = SM::kTile;
@@ -647,7 +653,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 
 template <int ES, int PL, int DM, bool FUSED, typename OffT, int RANK, class Cfg>
 cudaError_t launch_scatter_c(const ScatterParams &sp, int num_sms, cudaStream_t st) {
-	using SM = ScatterSmem<ES, PL, Cfg>;
+	using SM = ScatterSmem<ES, PL, Cfg, FUSED>;
 	auto kern = scatter_kernel<ES, PL, DM, FUSED, OffT, RANK, Cfg>;
 	static int occ_cache[64] = {}; // per device
 	int dev = 0;
@@ -664,7 +670,7 @@ cudaError_t launch_scatter_c(const ScatterParams &sp, int num_sms, cudaStream_t 
 		ctas_per_sm = occ > 0 ? occ : 1;
 	}
 	ScatterParams q = sp;
-	q.num_tiles = (uint32_t)((sp.n + SM::kTile - 1) / SM::kTile); // status rows are sized for the default tile (the smallest)
+	q.num_tiles = (uint32_t)((sp.n + SM::kTile - 1) / SM::kTile); // status rows are sized for the smallest tile (scatter_geometry)
 	uint32_t grid = (uint32_t)num_sms * (uint32_t)ctas_per_sm;
 	if (grid > q.num_tiles)
 		grid = q.num_tiles;
@@ -685,7 +691,10 @@ cudaError_t launch_scatter_r(const ScatterParams &sp, int num_sms, cudaStream_t 
 		default: break;
 		}
 	}
-	return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfg<ES, PL>>(sp, num_sms, st);
+	if constexpr (FUSED)
+		return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, FusedCfg<ES, PL>>(sp, num_sms, st);
+	else
+		return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfg<ES, PL>>(sp, num_sms, st);
 }
 
 template <int ES, int PL, int DM, typename OffT>
