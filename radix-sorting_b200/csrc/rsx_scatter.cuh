@@ -166,30 +166,36 @@ template <int T, int I, int MB, int LBK, bool ST> struct CfgT {
 	static constexpr int kThreads = T, kItems = I, kMinBlocks = MB, kLookback = LBK;
 	static constexpr bool kStage = ST;
 };
-// Defaults from the B200 sweeps recorded in profiles/r1_variants.md: the pass is bound by the
-// shared-memory/LSU data pipe, so the largest tile that still leaves two CTAs per SM (4-byte
-// records) or one fat CTA (wider records) wins: 512 x 22 fills 2 x 111.7 KB, 1024 x 11 fills 217 KB.
+// Defaults from the B200 sweeps recorded in profiles/r1_variants.md.  The pass is bound by the
+// shared-memory/LSU data pipe and by per-tile fixed costs (barriers, look-back), so the tile is as
+// large as shared memory allows: 4-byte footprints run 512 threads x 22 records with two CTAs per
+// SM (2 x 111.7 KB); wider footprints run ONE 512-thread CTA per SM with 192 / footprint records
+// per thread (8 bytes: 512 x 24, 96 KB staging + 96 KB sorted tile) -- fewer, fatter threads beat
+// 1024 x 11 by 9 % on u64 keys (16 instead of 32 warp histograms to zero, sum and rewrite per tile).
+// Look-back window: every tile reads 2 x LB x 256 status words in its first round (32 KB at LB 16
+// against a 45 KB tile of 4-byte keys); 8 words per thread cost a few more serial rounds but 7 % less
+// time per u32 pass (LB 4 / 6 / 8 / 12 / 16: 2.59 / 2.58 / 2.59 / 2.67 / 2.79 ms).
 template <int ES, int PL, int V> struct ScatterCfgV
-	: CfgT<((ES + PL > 4 && ES + PL <= 8) ? 1024 : 512),
-	       ((ES + PL <= 4) ? 22 : (ES + PL <= 8) ? 11 : (ES + PL <= 16) ? 8 : 4), ((ES + PL <= 4) ? 2 : 1), 16, true> {};
+	: CfgT<512, ((ES + PL <= 4) ? 22 : 192 / (ES + PL)), ((ES + PL <= 4) ? 2 : 1), 8, true> {};
 // The fused partition + exchange passes (multi-GPU) carry a 4 KB destination table in shared
 // memory and keep the geometry they were tuned and measured with.  It is the smallest tile of any
 // default kernel, so it also sizes the look-back state (scatter_geometry()).
 template <int ES, int PL> struct FusedCfg
 	: CfgT<((ES + PL > 4 && ES + PL <= 8) ? 1024 : 512),
-	       ((ES + PL <= 4) ? 20 : (ES + PL <= 8) ? 10 : (ES + PL <= 16) ? 8 : 4), ((ES + PL <= 4) ? 2 : 1), 16, true> {};
+	       ((ES + PL <= 4) ? 20 : (ES + PL <= 8) ? 10 : (ES + PL <= 16) ? 8 : 4), ((ES + PL <= 4) ? 2 : 1),
+	       ((ES + PL <= 4) ? 8 : 16), true> {};
 constexpr int kNumVariants = 6;
 // tuning variants exist for plain 4- and 8-byte keys only
-template <> struct ScatterCfgV<4, 0, 1> : CfgT<512, 20, 2, 16, true> {};
-template <> struct ScatterCfgV<4, 0, 2> : CfgT<512, 20, 2, 24, true> {};
-template <> struct ScatterCfgV<4, 0, 3> : CfgT<1024, 16, 1, 16, true> {};
-template <> struct ScatterCfgV<4, 0, 4> : CfgT<512, 24, 1, 16, true> {};
-template <> struct ScatterCfgV<4, 0, 5> : CfgT<512, 32, 1, 16, true> {};
-template <> struct ScatterCfgV<8, 0, 1> : CfgT<1024, 10, 1, 16, true> {};
-template <> struct ScatterCfgV<8, 0, 2> : CfgT<1024, 10, 1, 24, true> {};
-template <> struct ScatterCfgV<8, 0, 3> : CfgT<1024, 8, 1, 16, true> {};
-template <> struct ScatterCfgV<8, 0, 4> : CfgT<512, 12, 1, 16, true> {};
-template <> struct ScatterCfgV<8, 0, 5> : CfgT<512, 16, 1, 16, true> {};
+template <> struct ScatterCfgV<4, 0, 1> : CfgT<512, 22, 2, 16, true> {};
+template <> struct ScatterCfgV<4, 0, 2> : CfgT<512, 20, 2, 16, true> {};
+template <> struct ScatterCfgV<4, 0, 3> : CfgT<512, 22, 2, 4, true> {};
+template <> struct ScatterCfgV<4, 0, 4> : CfgT<512, 40, 1, 8, true> {};
+template <> struct ScatterCfgV<4, 0, 5> : CfgT<512, 44, 1, 8, true> {};
+template <> struct ScatterCfgV<8, 0, 1> : CfgT<1024, 11, 1, 12, true> {};
+template <> struct ScatterCfgV<8, 0, 2> : CfgT<1024, 10, 1, 16, true> {};
+template <> struct ScatterCfgV<8, 0, 3> : CfgT<512, 25, 1, 12, true> {};
+template <> struct ScatterCfgV<8, 0, 4> : CfgT<256, 48, 1, 8, true> {};
+template <> struct ScatterCfgV<8, 0, 5> : CfgT<384, 32, 1, 8, true> {};
 template <int ES, int PL> using ScatterCfg = ScatterCfgV<ES, PL, 0>;
 int scatter_variant();
 
