@@ -185,7 +185,9 @@ template <int ES, int PL> struct FusedCfg
 	       ((ES + PL <= 4) ? 20 : (ES + PL <= 8) ? 10 : (ES + PL <= 16) ? 8 : 4), ((ES + PL <= 4) ? 2 : 1),
 	       ((ES + PL <= 4) ? 8 : 16), true> {};
 constexpr int kNumVariants = 6;
-// tuning variants exist for plain 4- and 8-byte keys only
+// Tuning variants (bench.py --variant V, tools/gpu_ab.sh) exist for plain 4- and 8-byte keys only:
+// the neighbours of the default in the last sweep (profiles/r1_variants.md, "Final geometry"),
+// V = 2 being the geometry most of round 1 was measured with.
 template <> struct ScatterCfgV<4, 0, 1> : CfgT<512, 22, 2, 16, true> {};
 template <> struct ScatterCfgV<4, 0, 2> : CfgT<512, 20, 2, 16, true> {};
 template <> struct ScatterCfgV<4, 0, 3> : CfgT<512, 22, 2, 4, true> {};
