@@ -230,7 +230,8 @@ def main():
 
     if world > 1:
         dsort = importlib.import_module("radix-sorting_b200.dist")
-        result = dsort.bench_partitioned(args, rsx, tname, n, dname, mask, orv, rank, world, dev)
+        result = dsort.bench_partitioned(args, rsx, tname, n, dname, mask, orv, rank, world, dev,
+                                         sampler=ClockSampler(local_rank) if rank == 0 else None)
         if not explicit_workload:
             import copy
             a2 = copy.copy(args)
@@ -239,6 +240,10 @@ def main():
             torch.cuda.empty_cache()
             r2 = dsort.bench_partitioned(a2, rsx, t2, n2, d2, m2, o2, rank, world, dev)
             result["config5_u64"] = {k: r2[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "steps")}
+        peak, peak_src = measured_peak()
+        for r in (result, result.get("config5_u64")):
+            if r:  # whole partitioned sort per GPU against the measured HBM peak (the NVLink term is listed beside it)
+                r["roofline"].update(peak=peak, peak_source=peak_src, frac=r["roofline"]["achieved"] / peak)
         if rank == 0:
             print(json.dumps(result))
         dist.destroy_process_group()

@@ -367,7 +367,7 @@ def partitioned_sort(keys, kf, group=None, engine=None, timers: bool = False, fu
 
 
 # -------------------------------------------------------------------------------------------------
-def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world, dev):
+def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world, dev, sampler=None):
     """bench.py's N > 1 arm: weak scaling, n_per_gpu keys per rank, device-timed, max over ranks."""
     import torch
     import torch.distributed as dist
@@ -387,6 +387,8 @@ def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world
         keys.copy_(pristine)
         if it == args.warmup:
             launches0 = rsx.total_kernel_launches()
+            if sampler is not None:
+                sampler.start()  # nvidia-smi clocks / throttle reasons over the timed steps
         dist.barrier()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -400,6 +402,7 @@ def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world
             times.append(float(ms.item()))
         last = (res, info)
     launches = rsx.total_kernel_launches() - launches0
+    clocks = sampler.stop() if sampler is not None else None
     res, info = last
     # verification at full size: every shard ordered, shard boundaries ordered, multiset preserved
     d1, s1, x1 = rsx.verify(res, kf) if info.n_out > 1 else (0, 0, 0)
@@ -488,5 +491,5 @@ def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world
                      "note": "per-GPU algorithmic HBM bytes (histogram + partition pass + local LSD) over the step time; "
                              "NVLink term: each GPU sends/receives (N-1)/N of its shard",
                      "nvlink_bytes_per_gpu": n_per_gpu * kb * (world - 1) / world},
-        "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches),
+        "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
