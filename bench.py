@@ -113,48 +113,75 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_reference_run(tname, n, dist, mask, orv, repeats=1):
-    """Times the reference's CPU radix_sort (oracle/_ref when present, else the oracle port) on one
-    core -- the reference is single-threaded by construction.  Both buffers are pre-faulted."""
-    import numpy as np
-    import pyoracle
-    keygen = importlib.import_module("radix-sorting_b200.keygen")
-    t = pyoracle.TYPES[tname]
-    keys = np.empty(n, dtype=f"<u{t.key_bytes}")
-    CH = 1 << 24
-    for s in range(0, n, CH):
-        keys[s:s + CH] = keygen.fill(7, s, min(CH, n - s), t.key_bytes, dist, mask, orv)
-    src = keys.view(t.dtype)
-    aux = np.zeros_like(src)
-    try:
-        os.sched_setaffinity(0, {sorted(os.sched_getaffinity(0))[0]})
-    except Exception:
-        pass
-    best = None
-    if os.path.exists(pyoracle.LIB_REF):
-        ref, kind = pyoracle.Ref(), "reference"
-        for _ in range(repeats):
-            work = src.copy()
-            aux[:] = 0
-            t0 = time.perf_counter()
-            ref.radix_sort_inplace(t, work, aux)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-    else:
+SEED = 2  # every arm sorts the same stream: key i = keygen(SEED, i)
+
+
+def load_keygen():
+    """keygen.py by file path: the reference arm must not import the product package, whose
+    __init__ dlopens librsx.so."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("rsx_keygen", os.path.join(ROOT, "radix-sorting_b200", "keygen.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class CpuReference:
+    """The reference's CPU radix_sort (oracle/_ref when present, else the oracle port) on one core --
+    the reference is single-threaded by construction.  The sample is the first n keys of the stream
+    the GPU arm sorts (same seed, same bytes); both buffers are pre-faulted before the timed call
+    (the stock `./radix` malloc path counts the aux page faults)."""
+
+    def __init__(self, tname, n, dist, mask, orv):
+        import numpy as np
+        import pyoracle
+        keygen = load_keygen()
+        self.np, self.t, self.n, self.tname, self.dist = np, pyoracle.TYPES[tname], n, tname, dist
+        keys = np.empty(n, dtype=f"<u{self.t.key_bytes}")
+        CH = 1 << 24
+        for s in range(0, n, CH):
+            keys[s:s + CH] = keygen.fill(SEED, s, min(CH, n - s), self.t.key_bytes, dist, mask, orv)
+        self.src = keys.view(self.t.dtype)
+        self.work = np.empty_like(self.src)
+        self.aux = np.zeros_like(self.src)
+        try:
+            os.sched_setaffinity(0, {sorted(os.sched_getaffinity(0))[0]})
+        except Exception:
+            pass
+        if os.path.exists(pyoracle.LIB_REF):
+            self.ref, self.kind = pyoracle.Ref(), "reference"
+        else:
+            self.ref, self.kind = pyoracle.Oracle(), "port"
+        self.out = None
+
+    def run(self):
+        """One timed radix_sort call; returns seconds.  self.out is the sorted array."""
         import ctypes as C
-        orc, kind = pyoracle.Oracle(), "port"
-        L = t.layout()
-        for _ in range(repeats):
-            work = src.copy()
-            aux[:] = 0
+        np = self.np
+        np.copyto(self.work, self.src)
+        self.aux[:] = 0
+        if self.kind == "reference":
             t0 = time.perf_counter()
-            orc.L.orc_radix_sort(work.ctypes.data_as(C.c_void_p), aux.ctypes.data_as(C.c_void_p), n,
-                                 C.byref(L), None, None)
+            in_aux = self.ref.radix_sort_inplace(self.t, self.work, self.aux)
             dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-    return {"value": n / best / 1e9, "unit": "Gkeys/s", "cores": 1, "kind": kind,
-            "sample": f"{n} {tname} keys ({dist}), one radix_sort call, buffers pre-faulted, best of {repeats}",
-            "seconds": best, "host_cpus": os.cpu_count()}
+        else:
+            L = self.t.layout()
+            t0 = time.perf_counter()
+            resp = self.ref.L.orc_radix_sort(self.work.ctypes.data_as(C.c_void_p), self.aux.ctypes.data_as(C.c_void_p),
+                                             self.n, C.byref(L), None, None)
+            dt = time.perf_counter() - t0
+            in_aux = resp == self.aux.ctypes.data
+        self.out = self.aux if in_aux else self.work
+        return dt
+
+    def describe(self, seconds, repeats):
+        return {"value": self.n / seconds / 1e9, "unit": "Gkeys/s", "cores": 1, "kind": self.kind,
+                "sample": f"first {self.n} keys of the {self.tname} stream the GPU arm sorts (seed {SEED}, {self.dist}), "
+                          f"one radix_sort call, buffers pre-faulted, best of {repeats}",
+                "sample_keys": self.n, "seconds": seconds, "host_cpus": os.cpu_count(),
+                "build": ("oracle/_ref: the unmodified reference headers, g++ -O3 -march=x86-64-v3 -funroll-loops (built in "
+                          "the CPU container for the GPU box's host, hence not -march=native)")
+                if self.kind == "reference" else "oracle/rsx_oracle.c port"}
 
 
 def run_reference_arm(args, rank, world):
@@ -163,91 +190,52 @@ def run_reference_arm(args, rank, world):
     tname, n_full, dist, mask, orv, passes = WORKLOADS[args.workload]
     import pyoracle
     kb = pyoracle.TYPES[tname].key_bytes
-    n = min(n_full, CPU_SAMPLE_KEYS[kb] // 4)  # each step is a bounded sample; K+W of them must end in minutes
+    # Each step is a bounded sample: the reference needs ~25-45 s for 1 B u32 keys on one core, and
+    # K + W steps must end within a few minutes.  The rate is per key, the sample is stated.
+    budget_s = 150.0
+    per_key_s = {1: 1 / 150e6, 2: 1 / 80e6, 4: 1 / 40e6, 8: 1 / 12e6}[kb]
+    n = int(min(n_full, CPU_SAMPLE_KEYS[kb], max(1 << 22, budget_s / max(1, args.warmup + args.steps) / per_key_s)))
+    cpu = CpuReference(tname, n, dist, mask, orv)
     times = []
-    last = None
     for i in range(args.warmup + args.steps):
-        last = cpu_reference_run(tname, n, dist, mask, orv, repeats=1)
+        dt = cpu.run()
         if i >= args.warmup:
-            times.append(last["seconds"])
+            times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     val = n / (ms / 1e3) / 1e9
-    last["value"] = val
-    last["sample"] = f"{n} of {n_full} {tname} keys per step, one radix_sort call per step"
+    desc = cpu.describe(ms / 1e3, 1)
+    desc["sample"] = f"first {n} of {n_full} {tname} keys per step (seed {SEED}), one radix_sort call per step, mean of steps"
     print(json.dumps({
         "impl": "reference", "metric": "Gkeys/s sorted", "value": val, "unit": "Gkeys/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": tname, "data": "synthetic",
-        "config": {"workload": args.workload, "keys_per_step": n, "note": "reference CPU path, 1 core (single-threaded by construction)"},
-        "cpu_baseline": last,
+        "config": {"workload": args.workload, "keys": n_full, "keys_per_step": n, "same_config": n == n_full,
+                   "note": "reference CPU path, 1 core (single-threaded by construction); each step sorts the first "
+                           "keys_per_step keys of the workload's stream (bounded sample; Gkeys/s is a per-key rate)"},
+        "cpu_baseline": desc,
         "e2e": {"value": val, "unit": "Gkeys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default=None)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-fused", action="store_true", help="N > 1: NCCL all_to_all instead of fused peer stores")
-    ap.add_argument("--rank-mode", type=int, default=-1, help="-1 auto (hardware probe), 0 ticket, 1 ballot")
-    ap.add_argument("--variant", type=int, default=0, help="scatter tuning variant (rsx_scatter.cuh)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+def load_traffic(kb):
+    """DRAM bytes of one scatter launch from the committed ncu --set full capture (newest round first)."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", name)))["scatter_kernel"]["u32" if kb == 4 else "u64"]
+            return tj, name
+        except Exception:
+            continue
+    return None, None
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    explicit_workload = args.workload is not None
-    if args.workload is None:
-        # same per-GPU workload at every N (weak scaling): BASELINE configs[1]; at N > 1 the shards
-        # are sorted GLOBALLY (partition + NVLink all-to-all + local LSD) and configs[4]
-        # (2 B u64 keys per GPU) is measured as an extra line inside the JSON.
-        args.workload = "1B-u32-uniform"
 
-    if args.impl == "reference":
-        run_reference_arm(args, rank, world)
-        return
-
+def bench_single(args, rsx, torch, workload, dev, steps, warmup, do_e2e, do_cpu):
+    """One workload on one GPU: device-resident steps (value), per-kernel roofline, optional e2e
+    through host buffers and the CPU reference beside it.  Returns the JSON-able dict."""
     import numpy as np
-    import torch
-    import torch.distributed as dist
-    rsx = importlib.import_module("radix-sorting_b200")  # raises if librsx.so is missing: no fallback
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU path"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    tname, n, dname, mask, orv, passes = WORKLOADS[args.workload]
+    tname, n, dname, mask, orv, passes = WORKLOADS[workload]
     tdt = _torch_dtype(torch, tname)
     kf = rsx.default_kdf(tdt) if tname[0] != "u" else rsx.KeyFunc(rsx.KDF_UNSIGNED)
     kb = torch.empty(0, dtype=tdt).element_size()
-
-    if world > 1:
-        dsort = importlib.import_module("radix-sorting_b200.dist")
-        result = dsort.bench_partitioned(args, rsx, tname, n, dname, mask, orv, rank, world, dev,
-                                         sampler=ClockSampler(local_rank) if rank == 0 else None)
-        if not explicit_workload:
-            import copy
-            a2 = copy.copy(args)
-            a2.workload, a2.steps, a2.warmup, a2.no_e2e = "2B-u64-uniform", min(args.steps, 3), 3, True
-            t2, n2, d2, m2, o2, _ = WORKLOADS[a2.workload]
-            torch.cuda.empty_cache()
-            r2 = dsort.bench_partitioned(a2, rsx, t2, n2, d2, m2, o2, rank, world, dev)
-            result["config5_u64"] = {k: r2[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "steps")}
-        peak, peak_src = measured_peak()
-        for r in (result, result.get("config5_u64")):
-            if r:  # whole partitioned sort per GPU against the measured HBM peak (the NVLink term is listed beside it)
-                r["roofline"].update(peak=peak, peak_source=peak_src, frac=r["roofline"]["achieved"] / peak)
-        if rank == 0:
-            print(json.dumps(result))
-        dist.destroy_process_group()
-        return
 
     # three full-size buffers (pristine, src, aux) do not fit for the 8 B-key strong-scaling base:
     # there the input is regenerated in place before every step instead of copied back
@@ -258,10 +246,10 @@ def main():
         pristine = None
 
         def restore():
-            rsx.fill_keys(src, seed=2 + rank, dist=dname, mask=mask, orv=orv)
+            rsx.fill_keys(src, seed=SEED, dist=dname, mask=mask, orv=orv)
     else:
         pristine = torch.empty_like(src)
-        rsx.fill_keys(pristine, seed=2 + rank, dist=dname, mask=mask, orv=orv)
+        rsx.fill_keys(pristine, seed=SEED, dist=dname, mask=mask, orv=orv)
 
         def restore():
             src.copy_(pristine)
@@ -283,25 +271,28 @@ def main():
         e1.synchronize()
         return e0.elapsed_time(e1), rep, res, rsx.get_profile()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         _, rep, res, _ = step()
     d1, s1, x1 = rsx.verify(res, kf)
     assert d1 == 0 and (s1, x1) == (s0, x0), "warm-up result is not a sorted permutation of the input"
     assert rep.ncols == passes, (rep.ncols, passes)
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(dev.index or 0)
     torch.cuda.synchronize()
     sampler.start()
     launches0 = rsx.total_kernel_launches()
     times, profs = [], []
     torch.cuda.synchronize()
-    for _ in range(args.steps):
+    for _ in range(steps):
         ms, rep, res, prof = step()
         times.append(ms)
         profs.append(prof)
     torch.cuda.synchronize()
     launches = rsx.total_kernel_launches() - launches0
     clocks = sampler.stop()
+    d1, s1, x1 = rsx.verify(res, kf)
+    verified = d1 == 0 and (s1, x1) == (s0, x0)
+    assert verified, "timed result is not a sorted permutation of the input"
 
     ms_per_step = sum(times) / len(times)
     value = n / (ms_per_step * 1e-3) / 1e9
@@ -315,21 +306,20 @@ def main():
     achieved = alg_bytes_pass / (avg_pass * 1e-3) / 1e9
     alg_bytes_sort = n * kb * (1 + 2 * passes)
     traffic, traffic_src = None, None
-    try:  # DRAM bytes of this kernel from the committed ncu --set full capture, scaled to this n
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["scatter_kernel"]["u32" if kb == 4 else "u64"]
+    tj, tname_file = load_traffic(kb)
+    if tj:  # DRAM bytes of this kernel from the committed ncu --set full capture, scaled to this n
         traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * n / tj["keys"]
-        traffic_src = "dram__bytes_read.sum + dram__bytes_write.sum of one launch at 256 M keys (profiles/r1_final_ncu.md), scaled by n"
-    except Exception:
-        pass
+        traffic_src = (f"dram__bytes_read.sum + dram__bytes_write.sum of one launch at {tj['keys']} keys "
+                       f"(profiles/{tname_file}), scaled by n")
+    hist_avg = sum(hist_ms) / len(hist_ms)
     roofline = {
         "bound": "hbm", "kernel": "scatter_kernel (K3, one launch per live column)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "traffic_source": traffic_src,
         "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_pass, "ms_per_launch": avg_pass,
-        "launches_timed": len(pass_ms),
-        "histogram_kernel": {"ms": sum(hist_ms) / len(hist_ms), "alg_bytes": n * kb,
-                             "achieved": n * kb / (sum(hist_ms) / len(hist_ms) * 1e-3) / 1e9,
-                             "frac": n * kb / (sum(hist_ms) / len(hist_ms) * 1e-3) / 1e9 / peak},
+        "launches_timed": len(pass_ms), "share_of_step": avg_pass * passes / ms_per_step,
+        "histogram_kernel": {"ms": hist_avg, "alg_bytes": n * kb, "achieved": n * kb / (hist_avg * 1e-3) / 1e9,
+                             "frac": n * kb / (hist_avg * 1e-3) / 1e9 / peak},
         "whole_sort": {"alg_bytes": alg_bytes_sort, "achieved": alg_bytes_sort / (ms_per_step * 1e-3) / 1e9,
                        "frac": alg_bytes_sort / (ms_per_step * 1e-3) / 1e9 / peak,
                        "frac_of_nominal_8TBs": alg_bytes_sort / (ms_per_step * 1e-3) / 1e9 / 8000.0},
@@ -337,42 +327,140 @@ def main():
 
     # ---- e2e: the same sort through the C ABI with HOST buffers (H2D + sort + D2H timed) ----------
     e2e = None
-    if not args.no_e2e and not regen:
+    if do_e2e and not regen:
+        res_dev = res.clone()  # the device-resident answer, to memcmp the e2e output against
         del src, aux
         torch.cuda.empty_cache()
         h_src = torch.empty(n, dtype=tdt, pin_memory=True)
         h_aux = torch.empty(n, dtype=tdt, pin_memory=True)
         h_pristine = pristine.cpu()
+        e2e_steps = max(5, steps)
         e2e_times = []
-        for i in range(1 + min(3, args.steps)):
+        for i in range(1 + e2e_steps):
             h_src.copy_(h_pristine)
             t0 = time.perf_counter()
             res_h = rsx.radix_sort(h_src, h_aux, None, kf)
             dt = time.perf_counter() - t0
             if i:
                 e2e_times.append(dt)
-        chk = res_h[:: max(1, n // 1_000_000)].to(torch.float64 if tname[0] == "f" else torch.int64)
+        e2e_ok = bool(torch.equal(res_h.to(dev).view(torch.uint8), res_dev.view(torch.uint8)))
+        assert e2e_ok, "e2e (host-buffer) result differs from the device-resident result"
         e2e_s = sum(e2e_times) / len(e2e_times)
         e2e = {"value": n / e2e_s / 1e9, "unit": "Gkeys/s", "h2d_bytes_per_step": n * kb, "d2h_bytes_per_step": n * kb,
-               "ms_per_step": e2e_s * 1e3, "steps": len(e2e_times),
-               "note": "rsx_sort on pinned HOST buffers: H2D + sort + D2H inside the timed call (wall clock)"}
-        del h_src, h_aux, h_pristine, chk
+               "ms_per_step": e2e_s * 1e3, "steps": len(e2e_times), "verified": e2e_ok,
+               "note": "rsx_sort on pinned HOST buffers: H2D + sort + D2H inside the timed call (wall clock, mean); the "
+                       "three phases are serial (a radix sort needs every key before its first pass), so the two PCIe "
+                       "copies are most of it; output memcmp-equal to the device-resident result"}
+        del h_src, h_aux, h_pristine, res_dev, res_h
+    else:
+        del src, aux
 
+    # ---- the CPU reference beside it, on the same bytes, and a memcmp of the two outputs -----------
     cpu = None
-    if not args.no_cpu:
-        cpu = cpu_reference_run(tname, min(n, CPU_SAMPLE_KEYS[kb]), dname, mask, orv, repeats=1)
+    if do_cpu:
+        ns = min(n, CPU_SAMPLE_KEYS[kb])
+        ref = CpuReference(tname, ns, dname, mask, orv)
+        reps = 2
+        best = min(ref.run() for _ in range(reps))
+        cpu = ref.describe(best, reps)
+        # identical bytes.  Sort the same sample on the GPU and memcmp.
+        torch.cuda.empty_cache()
+        g_src = torch.empty(ns, dtype=tdt, device=dev)
+        rsx.fill_keys(g_src, seed=SEED, dist=dname, mask=mask, orv=orv)
+        assert g_src[:1 << 20].cpu().numpy().tobytes() == ref.src[:1 << 20].tobytes(), "host and device key streams differ"
+        g_res = rsx.radix_sort(g_src, torch.empty_like(g_src), None, kf)
+        same = g_res.cpu().numpy().tobytes() == np.ascontiguousarray(ref.out).tobytes()
+        assert same, "GPU output differs from the CPU reference's output on the same input"
+        cpu["gpu_output_memcmp_equal"] = bool(same)
+        del g_src, g_res, ref
 
-    out = {
-        "metric": "Gkeys/s sorted", "value": value, "unit": "Gkeys/s", "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+    del pristine
+    torch.cuda.empty_cache()
+    return {
+        "metric": "Gkeys/s sorted", "value": value, "unit": "Gkeys/s", "n_gpus": 1, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": tname, "data": "synthetic",
-        "config": {"workload": args.workload, "keys": n, "key_bytes": kb, "live_passes": passes,
-                   "dist": dname, "rank_mode": rank_mode, "variant": args.variant, "l2": "inputs (n*key_bytes) larger than L2 and restored by a full-size copy before every step",
+        "config": {"workload": workload, "keys": n, "key_bytes": kb, "live_passes": passes, "seed": SEED,
+                   "dist": dname, "rank_mode": rank_mode, "variant": args.variant, "verified": bool(verified),
+                   "cpu_sample_keys": cpu["sample_keys"] if cpu else None,
+                   "l2": "inputs (n*key_bytes) larger than L2 and restored by a full-size copy before every step",
                    "timing": "CUDA events around each rsx_sort call on the launch stream, mean of steps",
                    "ms_min": min(times), "ms_max": max(times)},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks,
     }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (u64 / config 5 / zipf sub-lines)")
+    ap.add_argument("--no-fused", action="store_true", help="N > 1: NCCL all_to_all instead of fused peer stores")
+    ap.add_argument("--rank-mode", type=int, default=-1, help="-1 auto (hardware probe), 0 ticket, 1 ballot")
+    ap.add_argument("--variant", type=int, default=0, help="scatter tuning variant (rsx_scatter.cuh)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    explicit_workload = args.workload is not None
+    if args.workload is None:
+        # same per-GPU workload at every N (weak scaling): BASELINE configs[1]; at N > 1 the shards
+        # are sorted GLOBALLY (partition + NVLink all-to-all + local LSD) and configs[4]
+        # (2 B u64 keys per GPU, uniform and zipf) is measured as extra lines inside the JSON.
+        args.workload = "1B-u32-uniform"
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    rsx = importlib.import_module("radix-sorting_b200")  # raises if librsx.so is missing: no fallback
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU path"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    if world > 1:
+        import copy
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        dsort = importlib.import_module("radix-sorting_b200.dist")
+        tname, n, dname, mask, orv, passes = WORKLOADS[args.workload]
+        result = dsort.bench_partitioned(args, rsx, tname, n, dname, mask, orv, rank, world, dev,
+                                         sampler=ClockSampler(local_rank) if rank == 0 else None)
+        extras = {}
+        if not explicit_workload and not args.no_extra:
+            for key, wl in (("config5_u64", "2B-u64-uniform"), ("config5_u64_zipf", "2B-u64-zipf")):
+                a2 = copy.copy(args)
+                a2.workload, a2.steps, a2.warmup, a2.no_e2e = wl, min(args.steps, 3), 3, True
+                t2, n2, d2, m2, o2, _ = WORKLOADS[wl]
+                torch.cuda.empty_cache()
+                r2 = dsort.bench_partitioned(a2, rsx, t2, n2, d2, m2, o2, rank, world, dev,
+                                             sampler=ClockSampler(local_rank) if rank == 0 else None)
+                extras[key] = {k: r2[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "steps", "clocks")}
+        result.update(extras)
+        peak, peak_src = measured_peak()
+        for r in [result] + list(extras.values()):
+            # whole partitioned sort per GPU against the measured HBM peak (the NVLink term is listed beside it)
+            r["roofline"].update(peak=peak, peak_source=peak_src, frac=r["roofline"]["achieved"] / peak)
+        if rank == 0:
+            print(json.dumps(result))
+        dist.destroy_process_group()
+        return
+
+    out = bench_single(args, rsx, torch, args.workload, dev, args.steps, args.warmup, not args.no_e2e, not args.no_cpu)
+    if not explicit_workload and not args.no_extra:
+        # the u64 half of BASELINE's "u32/u64" metric, same contract, fewer steps
+        r64 = bench_single(args, rsx, torch, "1B-u64-uniform", dev, min(args.steps, 5), 3, False, False)
+        out["u64_1B"] = {k: r64[k] for k in ("value", "unit", "ms_per_step", "steps", "dtype", "config", "roofline",
+                                              "gpu_launches", "clocks")}
     print(json.dumps(out))
 
 

@@ -38,6 +38,10 @@ class OrcReport(C.Structure):
 REC16_U8 = np.dtype([("key", "u1"), ("pad", "V7"), ("name", "<u8")])       # radix_tests.cpp:15-18
 REC8_U32 = np.dtype([("key", "<u4"), ("payload", "<u4")])                   # config C4b
 REC16_U64 = np.dtype([("key", "<u8"), ("payload", "<u8")])                  # u64 key + 8 B payload
+# layouts the reference can express with a by-member KeyFunc but does not ship a test for
+# (no ref_code: checked against the oracle's independent stable sort, not against ref_shim)
+REC16_F64 = np.dtype([("payload", "<u8"), ("key", "<f8")])                  # double key in the 2nd word
+REC16_F32 = np.dtype([("payload", "<u4"), ("key", "<f4"), ("pad", "V8")])   # float key at offset 4
 
 
 @dataclass(frozen=True)
@@ -69,6 +73,8 @@ TYPES = {t.name: t for t in [
     ElemType("rec16_u8", REC16_U8, 16, 0, 1, KDF_UNSIGNED, 10),
     ElemType("rec8_u32", REC8_U32, 8, 0, 4, KDF_UNSIGNED, 11),
     ElemType("rec16_u64", REC16_U64, 16, 0, 8, KDF_UNSIGNED, 12),
+    ElemType("rec16_f64", REC16_F64, 16, 8, 8, KDF_FLOAT, -1),
+    ElemType("rec16_f32", REC16_F32, 16, 4, 4, KDF_FLOAT, -1),
 ]}
 
 
@@ -174,6 +180,8 @@ class Ref:
         L.ref_record_bytes.argtypes = [C.c_int]
         self.L = L
         for t in TYPES.values():
+            if t.ref_code < 0:
+                continue  # not instantiated in ref_shim.cpp
             assert L.ref_record_bytes(t.ref_code) == t.record_bytes == t.dtype.itemsize, t.name
 
     @staticmethod

@@ -133,9 +133,20 @@ struct Lease {
 	Ctl *pinned = nullptr;
 	bool cached = false;
 	bool own_pinned = false;
+	// Set once kernels that use the leased memory have been enqueued; cleared by the final
+	// synchronising read-back.  If a call fails in between, the destructor drains the stream
+	// before another host thread can be handed the same workspace.
+	cudaStream_t inflight = nullptr;
+	bool has_inflight = false;
+	void enqueued(cudaStream_t st) { inflight = st; has_inflight = true; }
+	void drained() { has_inflight = false; }
 	~Lease() {
 		if (dev < 0)
 			return;
+		if (has_inflight) {
+			cudaStreamSynchronize(inflight);
+			(void)cudaGetLastError();
+		}
 		if (cached) {
 			std::lock_guard<std::mutex> lk(g_dev[dev].mu);
 			g_dev[dev].busy = false;
@@ -154,9 +165,15 @@ struct StageLease {
 	int dev = -1;
 	void *ptr = nullptr;
 	bool cached = false;
+	cudaStream_t inflight = nullptr;
+	bool has_inflight = false;
 	~StageLease() {
 		if (dev < 0)
 			return;
+		if (has_inflight) { // a failed call may leave copies / kernels running on the staging buffer
+			cudaStreamSynchronize(inflight);
+			(void)cudaGetLastError();
+		}
 		if (cached) {
 			std::lock_guard<std::mutex> lk(g_dev[dev].mu);
 			g_dev[dev].stage_busy = false;
@@ -263,6 +280,13 @@ int ptr_kind(const void *p, PtrKind *k) {
 	if (e != cudaSuccess)
 		return fail_cuda(e, "cudaPointerGetAttributes");
 	*k = (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? PK_DEVICE : PK_HOST;
+	if (a.type == cudaMemoryTypeDevice) { // kernels are launched on the CURRENT device
+		int dev = -1;
+		if (cudaGetDevice(&dev) == cudaSuccess && a.device != dev) {
+			snprintf(t_err, sizeof(t_err), "pointer %p belongs to device %d, the current device is %d", p, a.device, dev);
+			return RSX_ERR_INVALID;
+		}
+	}
 	return RSX_OK;
 }
 
@@ -344,11 +368,12 @@ int enqueue_passes(const PassBuffers &pb, const Plan &P, unsigned char *wsp, int
 	return RSX_OK;
 }
 
-int read_ctl(const unsigned char *wsp, Ctl *pinned, cudaStream_t st, unsigned long long launches0,
-             rsx_report *rep, bool staged) {
-	const WsHead *ws = reinterpret_cast<const WsHead *>(wsp);
+int read_ctl(Lease &L, cudaStream_t st, unsigned long long launches0, rsx_report *rep, bool staged) {
+	const WsHead *ws = static_cast<const WsHead *>(L.ptr);
+	Ctl *pinned = L.pinned;
 	CU(cudaMemcpyAsync(pinned, &ws->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	L.drained();
 	prof_collect();
 	if (rep) {
 		rep->early_exit = pinned->early_exit;
@@ -592,6 +617,7 @@ static int sort_device(void *src, void *aux, size_t n, const rsx_layout *layout,
 		int r = acquire(L, dev, sizeof(WsHead) + 256);
 		if (r)
 			return r;
+		L.enqueued(st);
 		WsHead *ws = static_cast<WsHead *>(L.ptr);
 		prof_mark(st, true);
 		CU(launch_small_sort(src, src, aux, nullptr, 0, n, layout->record_bytes, kd, &ws->ctl, st));
@@ -599,7 +625,7 @@ static int sort_device(void *src, void *aux, size_t n, const rsx_layout *layout,
 		rsx_report local;
 		if (!rep)
 			rep = &local;
-		if ((r = read_ctl(static_cast<unsigned char *>(L.ptr), L.pinned, st, l0, rep, staged)))
+		if ((r = read_ctl(L, st, l0, rep, staged)))
 			return r;
 		*result = rep->result_in_aux ? aux : src;
 		return RSX_OK;
@@ -610,6 +636,7 @@ static int sort_device(void *src, void *aux, size_t n, const rsx_layout *layout,
 	int r = acquire(L, dev, P.total);
 	if (r)
 		return r;
+	L.enqueued(st);
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
 	const int sms = g_dev[dev].num_sms;
 	if ((r = enqueue_front(src, P, wsp, sms, st)))
@@ -623,7 +650,7 @@ static int sort_device(void *src, void *aux, size_t n, const rsx_layout *layout,
 	rsx_report local;
 	if (!rep)
 		rep = &local;
-	if ((r = read_ctl(wsp, L.pinned, st, l0, rep, staged)))
+	if ((r = read_ctl(L, st, l0, rep, staged)))
 		return r;
 	*result = rep->result_in_aux ? aux : src;
 	return RSX_OK;
@@ -674,6 +701,8 @@ int rsx_sort(void *src, void *aux, size_t n, const rsx_layout *layout, void **re
 	if (!rep)
 		rep = &local;
 	r = RSX_OK;
+	SL.inflight = st;
+	SL.has_inflight = true; // drained below on success, by ~StageLease on any failure
 	cudaError_t e = cudaMemcpyAsync(dsrc, src, bytes, cudaMemcpyHostToDevice, st);
 	if (e != cudaSuccess)
 		r = fail_cuda(e, "H2D");
@@ -687,8 +716,10 @@ int rsx_sort(void *src, void *aux, size_t n, const rsx_layout *layout, void **re
 		if (e != cudaSuccess)
 			r = fail_cuda(e, "D2H");
 	}
-	if (!r)
+	if (!r) {
+		SL.has_inflight = false; // sort_device / the D2H copy synchronised the stream
 		*result = rep->result_in_aux ? aux : src;
+	}
 	return r;
 }
 
@@ -701,6 +732,7 @@ static int rank_device(const void *src, void *ib, size_t n, const rsx_layout *la
 		int r = acquire(L, dev, sizeof(WsHead) + 256);
 		if (r)
 			return r;
+		L.enqueued(st);
 		WsHead *wsh = static_cast<WsHead *>(L.ptr);
 		prof_mark(st, true);
 		CU(launch_small_sort(src, nullptr, nullptr, ib, idx_bytes, n, layout->record_bytes, kd, &wsh->ctl, st));
@@ -708,7 +740,7 @@ static int rank_device(const void *src, void *ib, size_t n, const rsx_layout *la
 		rsx_report local;
 		if (!rep)
 			rep = &local;
-		if ((r = read_ctl(static_cast<unsigned char *>(L.ptr), L.pinned, st, l0, rep, staged)))
+		if ((r = read_ctl(L, st, l0, rep, staged)))
 			return r;
 		*result = static_cast<unsigned char *>(ib) + (rep->result_in_aux ? n * (size_t)idx_bytes : 0);
 		return RSX_OK;
@@ -719,6 +751,7 @@ static int rank_device(const void *src, void *ib, size_t n, const rsx_layout *la
 	int r = acquire(L, dev, P.total);
 	if (r)
 		return r;
+	L.enqueued(st);
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
 	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
 	const int sms = g_dev[dev].num_sms;
@@ -748,7 +781,7 @@ static int rank_device(const void *src, void *ib, size_t n, const rsx_layout *la
 	rsx_report local;
 	if (!rep)
 		rep = &local;
-	if ((r = read_ctl(wsp, L.pinned, st, l0, rep, staged)))
+	if ((r = read_ctl(L, st, l0, rep, staged)))
 		return r;
 	*result = rep->result_in_aux ? ibb + n * (size_t)idx_bytes : ibb; // radix_sort_rank.hpp:91
 	return RSX_OK;
@@ -802,6 +835,8 @@ int rsx_sort_rank(const void *src, void *index_buffer, size_t n, const rsx_layou
 	if (!rep)
 		rep = &local;
 	r = RSX_OK;
+	SL.inflight = st;
+	SL.has_inflight = true;
 	cudaError_t e = cudaMemcpyAsync(dsrc, src, sbytes, cudaMemcpyHostToDevice, st);
 	if (e != cudaSuccess)
 		r = fail_cuda(e, "H2D");
@@ -816,8 +851,10 @@ int rsx_sort_rank(const void *src, void *index_buffer, size_t n, const rsx_layou
 		if (e != cudaSuccess)
 			r = fail_cuda(e, "D2H");
 	}
-	if (!r)
+	if (!r) {
+		SL.has_inflight = false;
 		*result = hres;
+	}
 	return r;
 }
 
@@ -845,6 +882,7 @@ int rsx_histogram(const void *src, size_t n, const rsx_layout *layout, uint64_t 
 	Lease L;
 	if ((r = acquire(L, dev, P.total)))
 		return r;
+	L.enqueued(st);
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
 	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
 	if ((r = enqueue_front(src, P, wsp, g_dev[dev].num_sms, st)))
@@ -852,7 +890,7 @@ int rsx_histogram(const void *src, size_t n, const rsx_layout *layout, uint64_t 
 	rsx_report local;
 	if (!rep)
 		rep = &local;
-	if ((r = read_ctl(wsp, L.pinned, st, l0, rep, false)))
+	if ((r = read_ctl(L, st, l0, rep, false)))
 		return r;
 	rep->live_mask = L.pinned->live_mask; // report the probe even when the input is presorted
 	rep->ncols = L.pinned->ncols;
@@ -884,6 +922,7 @@ int rsx_scatter_pass(const void *src, void *dst, const void *payload_src, void *
 	Lease L;
 	if ((r = acquire(L, dev, P.total)))
 		return r;
+	L.enqueued(st);
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
 	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
 	const int sms = g_dev[dev].num_sms;
@@ -899,6 +938,7 @@ int rsx_scatter_pass(const void *src, void *dst, const void *payload_src, void *
 	if ((r = run_scatter(pb, P, col, ws, true, wsp + P.off_status, &ws->tickets[col], sms, st)))
 		return r;
 	CU(cudaStreamSynchronize(st));
+	L.drained();
 	return RSX_OK;
 }
 
@@ -922,6 +962,7 @@ int rsx_scatter_pass_to(const void *src, size_t n, const rsx_layout *layout, int
 	Lease L;
 	if ((r = acquire(L, dev, P.total)))
 		return r;
+	L.enqueued(st);
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
 	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
 	const int sms = g_dev[dev].num_sms;
@@ -934,6 +975,7 @@ int rsx_scatter_pass_to(const void *src, size_t n, const rsx_layout *layout, int
 	CU(launch_scatter(pb, P.n, P.rb, 0, P.kd, col, ws, true, wsp + P.off_status, &ws->tickets[col], P.wide, sms, st,
 	                  ws->dest_base, ws->owner, nullptr, 0, ndest));
 	CU(cudaStreamSynchronize(st));
+	L.drained();
 	return RSX_OK;
 }
 
@@ -995,6 +1037,7 @@ int rsx_split_pass_to(const void *src, size_t n, const rsx_layout *layout, const
 	Lease L;
 	if ((r = acquire(L, dev, P.total)))
 		return r;
+	L.enqueued(st);
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
 	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
 	const int sms = g_dev[dev].num_sms;
@@ -1012,6 +1055,7 @@ int rsx_split_pass_to(const void *src, size_t n, const rsx_layout *layout, const
 	CU(launch_scatter(pb, P.n, P.rb, 0, P.kd, 0, ws, true, wsp + P.off_status, &ws->tickets[0], P.wide, sms, st,
 	                  ws->dest_base, ws->owner, reinterpret_cast<const unsigned long long *>(splitters), nsplit, nsplit + 1));
 	CU(cudaStreamSynchronize(st));
+	L.drained();
 	return RSX_OK;
 }
 

@@ -594,7 +594,12 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 					const uint32_t sl = tid < nhead ? beg + tid : a1 + (tid - nhead);
 					*reinterpret_cast<R *>(r0 + (unsigned long long)(sl - beg) * ES) = s_rec[sl];
 				}
-				if constexpr (ES < 16) {
+				if constexpr (ES == 16) {
+					// a 16-byte record is already one full vector and dest_base is record-aligned
+					R *rv = reinterpret_cast<R *>(r0);
+					for (uint32_t q = tid; q < end - beg; q += THREADS)
+						rv[q] = s_rec[beg + q];
+				} else {
 					const uint32_t shb = (a0 & (G - 1)) * ES;          // byte misalignment of the shared side
 					const uint32_t dw = shb >> 2, db = (shb & 3u) * 8u; // whole words + bits inside a word
 					const uint4 *sv = reinterpret_cast<const uint4 *>(s_rec + (a0 - (a0 & (G - 1))));
@@ -731,7 +736,7 @@ cudaError_t launch_scatter_pl(const ScatterParams &sp, bool is_float, bool wide,
 		else
 			return cudaErrorInvalidValue;
 	}
-	if constexpr (ES == 4 || ES == 8) {
+	if constexpr (ES == 4 || ES == 8 || ES == 16) { // a float/double key needs >= 4 bytes (check_layout)
 		if (is_float)
 			return wide ? launch_scatter_t<ES, PL, DIGIT_FLOAT, unsigned long long>(sp, num_sms, st)
 			            : launch_scatter_t<ES, PL, DIGIT_FLOAT, uint32_t>(sp, num_sms, st);

@@ -130,6 +130,13 @@ __global__ void split_counts_kernel(const typename Rec<ES>::type *__restrict__ d
 // Hardware probe behind RANK_TICKET (rsx_scatter.cuh): are same-address shared-memory atomicAdd
 // tickets of one warp instruction handed out in ascending lane order, and a warp's back-to-back
 // atomics applied in program order?  Compared against the ballot-derived stable rank.
+// The atomic is issued exactly the way the production kernels issue it (ptxas turns every one of
+// these into a -- possibly predicated -- ATOMS.POPC.INC, check with cuobjdump -sass):
+//   MODE 0  all 32 lanes, convergent
+//   MODE 1  scatter_kernel: lanes holding the tile's "hot" digit are ranked by a vote and skip
+//           the atomic (`if (is_hot) ... else atomicAdd`), a different lane subset per item
+//   MODE 2  small_sort_kernel: `valid ? atomicAdd(..) : 0` with a ragged tail of invalid lanes
+template <int MODE>
 __global__ void __launch_bounds__(512) ticket_probe_kernel(unsigned long long *mismatch, int iters, uint32_t digit_mask) {
 	constexpr int ITEMS = 16;
 	__shared__ uint32_t wh[16][kBins];
@@ -144,16 +151,35 @@ __global__ void __launch_bounds__(512) ticket_probe_kernel(unsigned long long *m
 #pragma unroll
 		for (int i = 0; i < ITEMS; ++i)
 			d[i] = (uint32_t)(mix64(((unsigned long long)blockIdx.x << 40) + ((unsigned long long)it << 20) + threadIdx.x * 64 + i) >> 24) & digit_mask;
+		// which lanes take part in item i's atomic
+		const uint32_t hot = __shfl_sync(0xFFFFFFFFu, d[0], it & 31); // some digit that occurs
+		const uint32_t nvalid = 1u + (uint32_t)(mix64((unsigned long long)it * 977u + blockIdx.x) % (ITEMS * 32u));
+		uint32_t hotcnt = 0;
 #pragma unroll
-		for (int i = 0; i < ITEMS; ++i)
-			ticket[i] = atomicAdd(&wh[warp][d[i]], 1u);
+		for (int i = 0; i < ITEMS; ++i) {
+			if constexpr (MODE == 0) {
+				ticket[i] = atomicAdd(&wh[warp][d[i]], 1u);
+			} else if constexpr (MODE == 1) {
+				const bool is_hot = d[i] == hot;
+				const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_hot);
+				if (is_hot)
+					ticket[i] = hotcnt + __popc(m & lt);
+				else
+					ticket[i] = atomicAdd(&wh[warp][d[i]], 1u);
+				hotcnt += __popc(m);
+			} else {
+				const bool valid = (uint32_t)i * 32u + lane < nvalid;
+				ticket[i] = valid ? atomicAdd(&wh[warp][d[i]], 1u) : 0u;
+			}
+		}
 		__syncwarp();
 		for (int b = lane; b < kBins; b += 32)
 			wh[warp][b] = 0;
 		__syncwarp();
 #pragma unroll
 		for (int i = 0; i < ITEMS; ++i) {
-			uint32_t peers = 0xFFFFFFFFu;
+			const bool valid = MODE != 2 || (uint32_t)i * 32u + lane < nvalid;
+			uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
 #pragma unroll
 			for (int b = 0; b < 8; ++b) {
 				const bool bit = (d[i] >> b) & 1u;
@@ -162,13 +188,13 @@ __global__ void __launch_bounds__(512) ticket_probe_kernel(unsigned long long *m
 			}
 			const uint32_t leader = __ffs(peers) - 1;
 			uint32_t old = 0;
-			if (lane == leader) {
+			if (valid && lane == leader) {
 				old = wh[warp][d[i]];
 				wh[warp][d[i]] = old + __popc(peers);
 			}
 			__syncwarp();
-			old = __shfl_sync(0xFFFFFFFFu, old, leader);
-			bad += ticket[i] != old + __popc(peers & lt);
+			old = __shfl_sync(0xFFFFFFFFu, old, valid ? leader : lane);
+			bad += valid && ticket[i] != old + __popc(peers & lt);
 		}
 		__syncwarp();
 	}
@@ -201,9 +227,13 @@ cudaError_t launch_split_counts(const void *data, size_t n, uint32_t record_byte
 }
 
 cudaError_t launch_ticket_probe(unsigned long long *d_mismatch, int num_sms, cudaStream_t st) {
-	for (uint32_t mask : {0xFFu, 0x0Fu, 0x01u, 0x00u})
-		ticket_probe_kernel<<<num_sms * 2, 512, 0, st>>>(d_mismatch, 32, mask);
-	count_launch(4);
+	// ~20 M tickets per launch; the offline probe (tools/probe_atoms.cu) runs billions
+	for (uint32_t mask : {0xFFu, 0x0Fu, 0x01u}) {
+		ticket_probe_kernel<0><<<num_sms, 512, 0, st>>>(d_mismatch, 16, mask);
+		ticket_probe_kernel<1><<<num_sms, 512, 0, st>>>(d_mismatch, 16, mask);
+		ticket_probe_kernel<2><<<num_sms, 512, 0, st>>>(d_mismatch, 16, mask);
+	}
+	count_launch(9);
 	return cudaGetLastError();
 }
 

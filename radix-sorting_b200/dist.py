@@ -451,7 +451,7 @@ def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world
         if int(okt.item()):
             h_in.copy_(pristine)
             e2e_t = []
-            for it in range(3):
+            for it in range(1 + max(5, args.steps)):
                 dist.barrier()
                 torch.cuda.synchronize(dev)
                 t0 = time.perf_counter()

@@ -20,7 +20,7 @@ def make_input(tname: str, n: int, seed: int, dist: str = "uniform", mask: int =
     if t.dtype.names is None:
         return keys.view(t.dtype).copy()
     out = np.zeros(n, dtype=t.dtype)
-    out["key"] = keys
+    out["key"] = keys.view(t.dtype["key"])
     second = [f for f in t.dtype.names if f not in ("key", "pad")][0]
     out[second] = np.arange(n, dtype=np.uint64).astype(t.dtype[second])
     return out

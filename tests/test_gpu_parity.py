@@ -367,7 +367,8 @@ def test_more_than_2_pow_30_keys(rsx, torch):
 
 # ---- fused partition + exchange pass (multi-GPU building block), on one device ----------------------------
 
-@pytest.mark.parametrize("tname,col", [("u32", 3), ("u64", 7), ("rec8_u32", 3), ("f32", 3)])
+@pytest.mark.parametrize("tname,col", [("u32", 3), ("u64", 7), ("rec8_u32", 3), ("f32", 3), ("rec16_u64", 7),
+                                       ("rec16_u8", 0), ("u16", 1), ("u8", 0)])
 def test_scatter_pass_to_destinations(rsx, torch, oracle, tname, col):
     """rsx_scatter_pass_to with three local 'destinations': each receives exactly the records whose
     routing bucket it owns, in an order that a stable local sort turns into the oracle's order."""
@@ -416,14 +417,14 @@ def test_more_than_2_pow_32_records(rsx, torch):
     assert int(hist.sum()) == n and descents == 0
 
 
-@pytest.mark.parametrize("tname", ["u32", "u64", "i64", "f32", "rec8_u32"])
+@pytest.mark.parametrize("tname", ["u32", "u64", "i64", "f32", "rec8_u32", "rec16_u64", "rec16_u8", "rec16_f64"])
 def test_key_range_routing(rsx, torch, oracle, tname):
     """rsx_split_counts / rsx_split_pass_to: destination = number of splitters <= derived key."""
     import importlib
     dsort = importlib.import_module("radix-sorting_b200.dist")
     t = TYPES[tname]
     n = 200003
-    data = make_input(tname, n, 77, "zipf" if tname in ("u32", "u64", "rec8_u32") else "uniform")
+    data = make_input(tname, n, 77, "zipf" if tname in ("u32", "u64", "rec8_u32", "rec16_u64") else "uniform")
     L = t.layout()
     derived = dsort.derive_np(np.ascontiguousarray(data).view(np.uint8).reshape(n, t.record_bytes), L)
     splitters = dsort.choose_splitters(derived[::37], 5)
@@ -438,6 +439,23 @@ def test_key_range_routing(rsx, torch, oracle, tname):
     for j in range(5):
         got = bufs[j][: counts[j] * t.record_bytes].cpu().numpy()
         assert got.tobytes() == data[dest == j].tobytes(), f"range {j}: not the stable sub-sequence"
+
+
+@pytest.mark.parametrize("tname", ["rec16_f64", "rec16_f32"])
+@pytest.mark.parametrize("n", [3001, 70001, 300007])
+def test_float_key_inside_16_byte_record(rsx, torch, oracle, tname, n):
+    """basic_kdfs::by_member<&Rec::float_member> on a 16-byte record: the float KDF
+    (radix_sort_basic_kdf.hpp:32-46) applied to a member, through the single-CTA kernel (n = 3001) and
+    the multi-kernel path alike (the latter used to reject this layout with RSX_ERR_CUDA)."""
+    t = TYPES[tname]
+    data = make_input(tname, n, 13, "uniform")
+    for desc in (False, True):
+        out, rep, _ = gpu_sort(rsx, torch, tname, data, descending=desc)
+        want, orep, _ = oracle.radix_sort(data, t.layout(descending=desc))
+        assert out.tobytes() == want.tobytes() and rep.result_in_aux == orep.result_in_aux
+    ranks, rrep, _ = gpu_rank(rsx, torch, tname, data, np.uint32)
+    wr, worep, _ = oracle.radix_sort_rank(data, t.layout(), np.uint32)
+    assert np.array_equal(ranks, wr) and rrep.result_in_aux == worep.result_in_aux
 
 
 def test_multipass_composite_key_like_listing5(rsx, torch, oracle):
