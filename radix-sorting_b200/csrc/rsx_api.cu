@@ -11,10 +11,11 @@
 // fails.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
-#include "rsx_scatter.cuh"
+#include "rsx_scatter_dispatch.cuh"
 
 namespace rsx {
 
@@ -395,7 +396,13 @@ void trivial_report(rsx_report *rep) {
 
 } // namespace
 
-static std::atomic<int> g_variant{0};
+// RSX_SCATTER_VARIANT=<v> in the environment preselects a tuning variant (test runs under a variant)
+static int variant_from_env() {
+	const char *e = getenv("RSX_SCATTER_VARIANT");
+	const int v = e ? atoi(e) : 0;
+	return (v >= 0 && (v < kNumVariants || variant_is_v2(v))) ? v : 0;
+}
+static std::atomic<int> g_variant{variant_from_env()};
 int scatter_variant() { return g_variant.load(std::memory_order_relaxed); }
 
 int rank_mode() {
@@ -426,16 +433,26 @@ PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes) {
 	if (record_bytes == ES && payload_bytes == PL && v == V)                                     \
 		take(ScatterCfgV<ES, PL, V>::kThreads, ScatterCfgV<ES, PL, V>::kItems,                   \
 		     ScatterSmem<ES, PL, ScatterCfgV<ES, PL, V>, false>::kBytes);
+#define GEO2V(ES, PL, V)                                                                         \
+	if (record_bytes == ES && payload_bytes == PL && v == kVariant2Base + V)                     \
+		take(Cfg2V<ES, PL, V>::kThreads, Cfg2V<ES, PL, V>::kItems, Scatter2Smem<ES, PL, Cfg2V<ES, PL, V>>::kBytes);
 #define GEO(ES, PL)                                                                              \
 	if (record_bytes == ES && payload_bytes == PL) {                                             \
 		static_assert(FusedCfg<ES, PL>::kThreads * FusedCfg<ES, PL>::kItems <=                   \
 		              ScatterCfg<ES, PL>::kThreads * ScatterCfg<ES, PL>::kItems, "fused tile must be the smallest"); \
 		take(FusedCfg<ES, PL>::kThreads, FusedCfg<ES, PL>::kItems, ScatterSmem<ES, PL, FusedCfg<ES, PL>, true>::kBytes); \
+		/* the register-resident kernel's default geometry (PreferV2 or variant 10) */            \
+		take(Cfg2V<ES, PL, 0>::kThreads, Cfg2V<ES, PL, 0>::kItems, Scatter2Smem<ES, PL, Cfg2V<ES, PL, 0>>::kBytes); \
 	}
 	GEO(1, 0) GEO(1, 4) GEO(1, 8) GEO(2, 0) GEO(2, 4) GEO(2, 8) GEO(4, 0) GEO(4, 4) GEO(4, 8)
 	GEO(8, 0) GEO(8, 4) GEO(8, 8) GEO(16, 0) GEO(16, 4) GEO(16, 8)
 	GEOV(4, 0, 1) GEOV(4, 0, 2) GEOV(4, 0, 3) GEOV(4, 0, 4) GEOV(4, 0, 5)
 	GEOV(8, 0, 1) GEOV(8, 0, 2) GEOV(8, 0, 3) GEOV(8, 0, 4) GEOV(8, 0, 5)
+	GEO2V(4, 0, 1) GEO2V(4, 0, 2) GEO2V(4, 0, 3) GEO2V(4, 0, 4) GEO2V(4, 0, 5) GEO2V(4, 0, 6) GEO2V(4, 0, 7) GEO2V(4, 0, 8) GEO2V(4, 0, 9)
+	GEO2V(4, 0, 10) GEO2V(4, 0, 11) GEO2V(4, 0, 12) GEO2V(4, 0, 13) GEO2V(4, 0, 14) GEO2V(4, 0, 15) GEO2V(4, 0, 16) GEO2V(4, 0, 17) GEO2V(4, 0, 18) GEO2V(4, 0, 19)
+	GEO2V(8, 0, 1) GEO2V(8, 0, 2) GEO2V(8, 0, 3) GEO2V(8, 0, 4) GEO2V(8, 0, 5) GEO2V(8, 0, 6) GEO2V(8, 0, 7) GEO2V(8, 0, 8) GEO2V(8, 0, 9)
+	GEO2V(8, 0, 10) GEO2V(8, 0, 11) GEO2V(8, 0, 12) GEO2V(8, 0, 13) GEO2V(8, 0, 14) GEO2V(8, 0, 15) GEO2V(8, 0, 16) GEO2V(8, 0, 17) GEO2V(8, 0, 18) GEO2V(8, 0, 19)
+#undef GEO2V
 #undef GEO
 #undef GEOV
 	g.tile = g.threads * g.items;
@@ -544,7 +561,7 @@ int rsx_set_option(const char *name, long value) {
 		return RSX_OK;
 	}
 	if (name && strcmp(name, "scatter_variant") == 0) { // tuning experiments, see rsx_scatter.cuh
-		if (value < 0 || value >= kNumVariants)
+		if (value < 0 || (value >= kNumVariants && !variant_is_v2((int)value)))
 			return RSX_ERR_INVALID;
 		g_variant.store((int)value);
 		return RSX_OK;

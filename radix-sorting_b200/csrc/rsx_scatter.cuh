@@ -692,72 +692,6 @@ cudaError_t launch_scatter_c(const ScatterParams &sp, int num_sms, cudaStream_t 
 	return cudaGetLastError();
 }
 
-template <int ES, int PL, int DM, bool FUSED, typename OffT, int RANK>
-cudaError_t launch_scatter_r(const ScatterParams &sp, int num_sms, cudaStream_t st) {
-	if constexpr ((ES == 4 || ES == 8) && PL == 0 && DM == DIGIT_PLAIN && !FUSED && RANK == RANK_TICKET && sizeof(OffT) == 4) {
-		switch (scatter_variant()) {
-		case 1: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 1>>(sp, num_sms, st);
-		case 2: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 2>>(sp, num_sms, st);
-		case 3: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 3>>(sp, num_sms, st);
-		case 4: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 4>>(sp, num_sms, st);
-		case 5: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 5>>(sp, num_sms, st);
-		default: break;
-		}
-	}
-	if constexpr (FUSED)
-		return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, FusedCfg<ES, PL>>(sp, num_sms, st);
-	else
-		return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfg<ES, PL>>(sp, num_sms, st);
-}
-
-template <int ES, int PL, int DM, typename OffT>
-cudaError_t launch_scatter_t(const ScatterParams &sp, int num_sms, cudaStream_t st) {
-	const bool ticket = rank_mode() == RANK_TICKET;
-	if (sp.dest_base != nullptr) { // fused partition + exchange (records only)
-		if constexpr (PL == 0)
-			return ticket ? launch_scatter_r<ES, PL, DM, true, OffT, RANK_TICKET>(sp, num_sms, st)
-			              : launch_scatter_r<ES, PL, DM, true, OffT, RANK_BALLOT>(sp, num_sms, st);
-		else
-			return cudaErrorInvalidValue;
-	}
-	if constexpr (DM == DIGIT_SPLIT)
-		return cudaErrorInvalidValue; // key-range routing exists in fused form only
-	else
-		return ticket ? launch_scatter_r<ES, PL, DM, false, OffT, RANK_TICKET>(sp, num_sms, st)
-		              : launch_scatter_r<ES, PL, DM, false, OffT, RANK_BALLOT>(sp, num_sms, st);
-}
-
-template <int ES, int PL>
-cudaError_t launch_scatter_pl(const ScatterParams &sp, bool is_float, bool wide, int num_sms, cudaStream_t st) {
-	if (sp.nsplit != 0) { // routing by key-range splitters (multi-GPU partition): records only
-		if constexpr (PL == 0)
-			return wide ? launch_scatter_t<ES, PL, DIGIT_SPLIT, unsigned long long>(sp, num_sms, st)
-			            : launch_scatter_t<ES, PL, DIGIT_SPLIT, uint32_t>(sp, num_sms, st);
-		else
-			return cudaErrorInvalidValue;
-	}
-	if constexpr (ES == 4 || ES == 8 || ES == 16) { // a float/double key needs >= 4 bytes (check_layout)
-		if (is_float)
-			return wide ? launch_scatter_t<ES, PL, DIGIT_FLOAT, unsigned long long>(sp, num_sms, st)
-			            : launch_scatter_t<ES, PL, DIGIT_FLOAT, uint32_t>(sp, num_sms, st);
-	}
-	if (is_float)
-		return cudaErrorInvalidValue;
-	return wide ? launch_scatter_t<ES, PL, DIGIT_PLAIN, unsigned long long>(sp, num_sms, st)
-	            : launch_scatter_t<ES, PL, DIGIT_PLAIN, uint32_t>(sp, num_sms, st);
-}
-
-template <int ES>
-cudaError_t launch_scatter_es(const ScatterParams &sp, int payload_bytes, bool is_float, bool wide,
-                              int num_sms, cudaStream_t st) {
-	switch (payload_bytes) {
-	case 0: return launch_scatter_pl<ES, 0>(sp, is_float, wide, num_sms, st);
-	case 4: return launch_scatter_pl<ES, 4>(sp, is_float, wide, num_sms, st);
-	case 8: return launch_scatter_pl<ES, 8>(sp, is_float, wide, num_sms, st);
-	}
-	return cudaErrorInvalidValue;
-}
-
 // one translation unit per record size (parallel builds)
 cudaError_t launch_scatter_1(const ScatterParams &, int, bool, bool, int, cudaStream_t);
 cudaError_t launch_scatter_2(const ScatterParams &, int, bool, bool, int, cudaStream_t);
