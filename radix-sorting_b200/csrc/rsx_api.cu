@@ -446,8 +446,8 @@ PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes) {
 	}
 	GEO(1, 0) GEO(1, 4) GEO(1, 8) GEO(2, 0) GEO(2, 4) GEO(2, 8) GEO(4, 0) GEO(4, 4) GEO(4, 8)
 	GEO(8, 0) GEO(8, 4) GEO(8, 8) GEO(16, 0) GEO(16, 4) GEO(16, 8)
-	GEOV(4, 0, 1) GEOV(4, 0, 2) GEOV(4, 0, 3) GEOV(4, 0, 4) GEOV(4, 0, 5)
-	GEOV(8, 0, 1) GEOV(8, 0, 2) GEOV(8, 0, 3) GEOV(8, 0, 4) GEOV(8, 0, 5)
+	GEOV(4, 0, 1) GEOV(4, 0, 2) GEOV(4, 0, 3) GEOV(4, 0, 4) GEOV(4, 0, 5) GEOV(4, 0, 6) GEOV(4, 0, 7) GEOV(4, 0, 8) GEOV(4, 0, 9)
+	GEOV(8, 0, 1) GEOV(8, 0, 2) GEOV(8, 0, 3) GEOV(8, 0, 4) GEOV(8, 0, 5) GEOV(8, 0, 6) GEOV(8, 0, 7) GEOV(8, 0, 8) GEOV(8, 0, 9)
 	GEO2V(4, 0, 1) GEO2V(4, 0, 2) GEO2V(4, 0, 3) GEO2V(4, 0, 4) GEO2V(4, 0, 5) GEO2V(4, 0, 6) GEO2V(4, 0, 7) GEO2V(4, 0, 8) GEO2V(4, 0, 9)
 	GEO2V(4, 0, 10) GEO2V(4, 0, 11) GEO2V(4, 0, 12) GEO2V(4, 0, 13) GEO2V(4, 0, 14) GEO2V(4, 0, 15) GEO2V(4, 0, 16) GEO2V(4, 0, 17) GEO2V(4, 0, 18) GEO2V(4, 0, 19)
 	GEO2V(8, 0, 1) GEO2V(8, 0, 2) GEO2V(8, 0, 3) GEO2V(8, 0, 4) GEO2V(8, 0, 5) GEO2V(8, 0, 6) GEO2V(8, 0, 7) GEO2V(8, 0, 8) GEO2V(8, 0, 9)

@@ -34,28 +34,6 @@ template <int T, int I, int MB, int LBK, int MD = 0> struct Cfg2T {
 	static constexpr int kThreads = T, kItems = I, kMinBlocks = MB, kLookback = LBK, kMode = MD;
 };
 
-// Predicated shared-memory ticket: lanes with take == false keep `r` (their vote-derived rank).
-// One predicated ATOMS instead of a divergent branch per item.
-__device__ __forceinline__ uint32_t ticket_unless(uint32_t *addr, bool skip, uint32_t r) {
-	asm volatile("{\n"
-	             ".reg .pred q;\n"
-	             "setp.eq.u32 q, %2, 0;\n"
-	             "@q atom.shared.add.u32 %0, [%1], 1;\n"
-	             "}\n"
-	             : "+r"(r)
-	             : "r"(smem_u32(addr)), "r"((uint32_t)skip)
-	             : "memory");
-	return r;
-}
-__device__ __forceinline__ void count_unless(uint32_t *addr, bool skip) {
-	asm volatile("{\n"
-	             ".reg .pred q;\n"
-	             "setp.eq.u32 q, %1, 0;\n"
-	             "@q red.shared.add.u32 [%0], 1;\n"
-	             "}\n" ::"r"(smem_u32(addr)), "r"((uint32_t)skip)
-	             : "memory");
-}
-
 template <int ES, int PL, class Cfg> struct Scatter2Smem {
 	static constexpr int kTile = Cfg::kThreads * Cfg::kItems;
 	static constexpr int kWarps = Cfg::kThreads / 32;
@@ -74,7 +52,8 @@ template <int ES, int PL, class Cfg> struct Scatter2Smem {
 // V = 0 is the default per footprint (record + payload bytes); V >= 1 are tuning variants for plain
 // 4- and 8-byte keys (rsx_set_option("scatter_variant", 10 + V), tools/sweep_variants.py).
 template <int ES, int PL, int V> struct Cfg2V
-	: Cfg2T<512, ((ES + PL <= 4) ? 22 : (ES + PL <= 8) ? 12 : (ES + PL <= 16) ? 8 : 6), 2, 8> {};
+	: Cfg2T<((ES + PL > 4 && ES + PL <= 8) ? 256 : 512),
+	        ((ES + PL <= 4) ? 22 : (ES + PL <= 8) ? 32 : (ES + PL <= 16) ? 8 : 6), 2, 8, ((ES + PL > 4 && ES + PL <= 8) ? 1 : 0)> {};
 constexpr int kNumVariants2 = 20;
 template <> struct Cfg2V<4, 0, 1> : Cfg2T<512, 20, 2, 8> {};
 template <> struct Cfg2V<4, 0, 2> : Cfg2T<384, 24, 2, 8> {};
@@ -119,6 +98,10 @@ template <> struct Cfg2V<8, 0, 19> : Cfg2T<384, 24, 2, 8, 1> {};
 // Which kernel runs a single-GPU pass when no variant is forced: flipped per footprint by
 // measurement (profiles/r2_variants.md).
 template <int ES, int PL> struct PreferV2 { static constexpr bool value = false; };
+// 8-byte records without a payload lane (u64 / i64 / f64 keys, {u32 key, u32 payload} records):
+// 256 threads x 32 records, two CTAs per SM, count + ticket placement -- 4.01 ms per pass of 1 B u64
+// keys against 4.22 ms for the staging kernel, which has room for only one CTA per SM.
+template <> struct PreferV2<8, 0> { static constexpr bool value = true; };
 
 // Streaming load: every record is read exactly once per pass.
 template <typename R> __device__ __forceinline__ R ld_stream(const R *p) { return __ldcs(p); }

@@ -55,6 +55,10 @@ cudaError_t launch_scatter_r(const ScatterParams &sp, int num_sms, cudaStream_t 
 		case 3: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 3>>(sp, num_sms, st);
 		case 4: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 4>>(sp, num_sms, st);
 		case 5: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 5>>(sp, num_sms, st);
+		case 6: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 6>>(sp, num_sms, st);
+		case 7: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 7>>(sp, num_sms, st);
+		case 8: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 8>>(sp, num_sms, st);
+		case 9: return launch_scatter_c<ES, PL, DM, FUSED, OffT, RANK, ScatterCfgV<ES, PL, 9>>(sp, num_sms, st);
 		default: break;
 		}
 	}
