@@ -401,6 +401,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (u64 / config 5 / zipf sub-lines)")
+    ap.add_argument("--no-selftest", action="store_true", help="N > 1: skip the oracle parity run before the timed steps")
     ap.add_argument("--no-fused", action="store_true", help="N > 1: NCCL all_to_all instead of fused peer stores")
     ap.add_argument("--rank-mode", type=int, default=-1, help="-1 auto (hardware probe), 0 ticket, 1 ballot")
     ap.add_argument("--variant", type=int, default=0, help="scatter tuning variant (rsx_scatter.cuh)")
@@ -433,6 +434,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         dsort = importlib.import_module("radix-sorting_b200.dist")
         tname, n, dname, mask, orv, passes = WORKLOADS[args.workload]
+        # on-hardware parity of exactly this code path, bytes against the CPU oracle
+        st = None
+        if not args.no_selftest:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            st = importlib.import_module("multi_gpu_selftest").selftest(rsx, rank, world, dev)
         result = dsort.bench_partitioned(args, rsx, tname, n, dname, mask, orv, rank, world, dev,
                                          sampler=ClockSampler(local_rank) if rank == 0 else None)
         extras = {}
@@ -446,6 +452,8 @@ def main():
                                              sampler=ClockSampler(local_rank) if rank == 0 else None)
                 extras[key] = {k: r2[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "steps", "clocks")}
         result.update(extras)
+        result["selftest"] = st
+        result["config"]["verified"] = bool(result["config"]["verified"] and (st is None or st["passed"]))
         peak, peak_src = measured_peak()
         for r in [result] + list(extras.values()):
             # whole partitioned sort per GPU against the measured HBM peak (the NVLink term is listed beside it)

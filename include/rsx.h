@@ -130,6 +130,97 @@ int rsx_split_counts(const void *src, size_t n, const rsx_layout *layout, const 
 int rsx_split_pass_to(const void *src, size_t n, const rsx_layout *layout, const uint64_t *splitters, int nsplit,
                       const uint64_t *dest_base, void *stream);
 
+/* ---- multi-GPU partitioned sort (BASELINE config 5) ----------------------
+ * No reference equivalent: eloj/radix-sorting is single-threaded host code.  This is the
+ * MSD-then-LSD composition of the entry points above over the GPUs of one box: per-shard
+ * histogram -> all-gather of the (columns x 256) counts -> routing of the top live digit's buckets
+ * (or of key ranges, for skewed keys) to ranks -> ONE fused partition + exchange pass that stores
+ * every record straight into its owner's receive buffer over NVLink -> local LSD sort.  The
+ * concatenation of the shards' outputs in rank order is bit-identical to radix_sort() of the
+ * concatenated input (stable across source ranks).
+ *
+ * The host orchestration is C++ inside librsx.so (csrc/rsx_multi.cu); the two collectives it needs
+ * are callbacks, so it runs as one process with a thread per GPU (rsx_sort_multi) or as one process
+ * per GPU under torchrun / MPI (rsx_sort_shard with the launcher's all-gather and barrier). */
+#define RSX_MAX_RANKS 16
+
+typedef struct rsx_comm {
+	int rank, world;
+	/* recv = world blocks of `bytes`, block g = rank g's `send`; HOST buffers */
+	int (*allgather)(void *ctx, const void *send, void *recv, size_t bytes);
+	/* every rank's device work issued so far is complete and visible to its peers */
+	int (*barrier)(void *ctx);
+	/* optional (non-fused exchange): DEVICE buffers, byte counts per peer, chunks in rank order */
+	int (*alltoallv)(void *ctx, const void *send, const uint64_t *send_bytes, void *recv, const uint64_t *recv_bytes);
+	void *ctx;
+} rsx_comm;
+
+/* Local primitives used by the orchestration.  NULL selects the CUDA kernels of this library; the
+ * table exists so that the CPU test-suite can run the same host logic over gloo with oracle-backed
+ * primitives (tests/test_dist.py) -- the product never substitutes them. */
+typedef struct rsx_shard_ops {
+	int (*hist)(void *ctx, const void *src, size_t n, const rsx_layout *L, uint64_t *hist /* key_bytes*256 */, void *stream);
+	int (*sample)(void *ctx, const void *src, size_t n, const rsx_layout *L, size_t count, uint64_t *derived, void *stream);
+	int (*split_counts)(void *ctx, const void *src, size_t n, const rsx_layout *L, const uint64_t *splitters, int nsplit,
+	                    uint64_t *counts, void *stream);
+	/* stable partition; destination D's records are appended at byte address dest_base[D].
+	 * col >= 0: destination = owner[digit of column col]; col < 0: key ranges (splitters) */
+	int (*partition_to)(void *ctx, const void *src, size_t n, const rsx_layout *L, int col, const uint8_t *owner,
+	                    const uint64_t *splitters, int nsplit, const uint64_t *dest_base, int ndest, void *stream);
+	int (*sort)(void *ctx, void *src, void *aux, size_t n, const rsx_layout *L, void **result, void *stream);
+	void *ctx;
+} rsx_shard_ops;
+
+/* Routing decision, a pure function of the all-gathered histograms (identical on every rank). */
+typedef struct rsx_route {
+	int32_t routing_column;              /* highest globally-live column, -1: nothing to route   */
+	uint32_t live_mask;                  /* columns that are not constant over all ranks          */
+	uint32_t key_range;                  /* 1: bucket ranges cannot balance, use key-range splitters */
+	uint32_t pad;
+	uint8_t owner[256];                  /* bucket -> rank, non-decreasing                         */
+	uint64_t n_in[RSX_MAX_RANKS];        /* shard sizes                                            */
+	uint64_t send_counts[RSX_MAX_RANKS]; /* this rank -> rank d                                    */
+	uint64_t recv_counts[RSX_MAX_RANKS]; /* rank g -> this rank                                    */
+	uint64_t dest_offset[RSX_MAX_RANKS]; /* record offset of this rank's chunk inside rank d's receive buffer */
+	uint64_t n_out, max_n_out, n_total;
+	double imbalance;                    /* max_n_out / (n_total / world)                          */
+} rsx_route;
+
+typedef struct rsx_multi_report {
+	int32_t routing_column;   /* -1: key-range routing or nothing routed */
+	uint32_t key_range;       /* 1: routed by sample-based key ranges    */
+	uint32_t live_mask;
+	uint32_t fused;           /* 1: records went straight into peer memory */
+	uint64_t n_total;
+	uint64_t needed_capacity; /* records each buffer must hold (valid also on RSX_ERR_WORKSPACE) */
+	double imbalance;
+	double seconds_histogram, seconds_routing, seconds_exchange, seconds_local_sort; /* host clock per phase */
+} rsx_multi_report;
+
+#define RSX_MULTI_NO_FUSED 1u     /* exchange through comm->alltoallv instead of peer stores */
+#define RSX_MULTI_NO_KEY_RANGE 2u /* always route by bucket ranges (tests)                  */
+
+int rsx_multi_route(const uint64_t *hist_all /* [world][cols][256] */, int world, int cols, int rank,
+                    double skew_threshold, rsx_route *out);
+int rsx_multi_splitters(const uint64_t *samples, size_t count, int world, uint64_t *splitters /* world-1 */);
+
+/* One rank's view.  `src` holds this rank's n records, `recv` is this rank's receive buffer; both
+ * hold `capacity` records and both are clobbered.  recv_peers[d] is rank d's receive buffer as
+ * THIS rank can address it (peer mapping; recv_peers[rank] == recv), or NULL for the non-fused
+ * exchange.  *result aliases src or recv and holds *n_out records.  If `capacity` is too small
+ * for the routed sizes every rank returns RSX_ERR_WORKSPACE before anything is moved and
+ * report->needed_capacity says what to allocate.  Collective: every rank must call it. */
+int rsx_sort_shard(const rsx_comm *comm, const rsx_shard_ops *ops /* NULL = CUDA */, void *src, size_t n, void *recv,
+                   void *const *recv_peers, size_t capacity, const rsx_layout *layout, uint32_t flags, void **result,
+                   size_t *n_out, rsx_multi_report *report, void *stream);
+
+/* One process, one host thread per GPU, peer access over NVLink.  src[g] / aux[g] live on
+ * devices[g] and hold `capacity` records each; shard g has n[g] records in src[g].  On return
+ * result[g] (src[g] or aux[g]) holds n_out[g] records.  reports: ngpus entries or NULL. */
+int rsx_sort_multi(int ngpus, const int *devices, void *const *src, void *const *aux, const size_t *n,
+                   size_t capacity, const rsx_layout *layout, uint32_t flags, void **result, size_t *n_out,
+                   rsx_multi_report *reports);
+
 /* ---- workspace ---------------------------------------------------------------------------
  * The reference allocates nothing (stack histograms).  The device path needs scratch for the
  * digit histograms, the pass table and the decoupled look-back state, and -- for rank sorts --

@@ -37,6 +37,7 @@ RSX_ERR_WORKSPACE, RSX_ERR_IDX_RANGE, RSX_ERR_MIXED_MEMORY = -4, -5, -6
 EXPORTS = [
     "rsx_sort", "rsx_sort_rank", "rsx_histogram", "rsx_scatter_pass", "rsx_scatter_pass_to",
     "rsx_split_counts", "rsx_split_pass_to",
+    "rsx_multi_route", "rsx_multi_splitters", "rsx_sort_shard", "rsx_sort_multi",
     "rsx_workspace_bytes",
     "rsx_reserve", "rsx_release", "rsx_fill_keys", "rsx_verify", "rsx_strerror",
     "rsx_last_cuda_error", "rsx_version", "rsx_total_kernel_launches", "rsx_set_option",
@@ -55,6 +56,52 @@ class RsxReport(C.Structure):
     _fields_ = [("early_exit", C.c_uint32), ("ncols", C.c_uint32), ("live_mask", C.c_uint32),
                 ("result_in_aux", C.c_uint32), ("kernel_launches", C.c_uint32),
                 ("staged", C.c_uint32)]
+
+
+RSX_MAX_RANKS = 16
+MULTI_NO_FUSED, MULTI_NO_KEY_RANGE = 1, 2
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+ALLTOALLV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64))
+
+
+class RsxComm(C.Structure):
+    """struct rsx_comm (include/rsx.h): the two collectives rsx_sort_shard needs, as callbacks."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("allgather", ALLGATHER_FN), ("barrier", BARRIER_FN),
+                ("alltoallv", ALLTOALLV_FN), ("ctx", C.c_void_p)]
+
+
+_LP = C.POINTER(RsxLayout)
+OPS_HIST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, _LP, C.POINTER(C.c_uint64), C.c_void_p)
+OPS_SAMPLE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, _LP, C.c_size_t, C.POINTER(C.c_uint64), C.c_void_p)
+OPS_SPLIT_COUNTS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, _LP, C.POINTER(C.c_uint64), C.c_int,
+                                  C.POINTER(C.c_uint64), C.c_void_p)
+OPS_PARTITION_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, _LP, C.c_int, C.POINTER(C.c_uint8),
+                               C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_uint64), C.c_int, C.c_void_p)
+OPS_SORT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, _LP, C.POINTER(C.c_void_p), C.c_void_p)
+
+
+class RsxShardOps(C.Structure):
+    """struct rsx_shard_ops: local primitives (NULL pointer = the library's CUDA kernels)."""
+    _fields_ = [("hist", OPS_HIST_FN), ("sample", OPS_SAMPLE_FN), ("split_counts", OPS_SPLIT_COUNTS_FN),
+                ("partition_to", OPS_PARTITION_FN), ("sort", OPS_SORT_FN), ("ctx", C.c_void_p)]
+
+
+class RsxRoute(C.Structure):
+    """struct rsx_route."""
+    _fields_ = [("routing_column", C.c_int32), ("live_mask", C.c_uint32), ("key_range", C.c_uint32), ("pad", C.c_uint32),
+                ("owner", C.c_uint8 * 256), ("n_in", C.c_uint64 * RSX_MAX_RANKS), ("send_counts", C.c_uint64 * RSX_MAX_RANKS),
+                ("recv_counts", C.c_uint64 * RSX_MAX_RANKS), ("dest_offset", C.c_uint64 * RSX_MAX_RANKS),
+                ("n_out", C.c_uint64), ("max_n_out", C.c_uint64), ("n_total", C.c_uint64), ("imbalance", C.c_double)]
+
+
+class RsxMultiReport(C.Structure):
+    """struct rsx_multi_report."""
+    _fields_ = [("routing_column", C.c_int32), ("key_range", C.c_uint32), ("live_mask", C.c_uint32), ("fused", C.c_uint32),
+                ("n_total", C.c_uint64), ("needed_capacity", C.c_uint64), ("imbalance", C.c_double),
+                ("seconds_histogram", C.c_double), ("seconds_routing", C.c_double), ("seconds_exchange", C.c_double),
+                ("seconds_local_sort", C.c_double)]
 
 
 class RsxError(RuntimeError):
@@ -96,6 +143,16 @@ def _lib() -> C.CDLL:
         L.rsx_split_counts.argtypes = [vp, sz, LP, u64p, C.c_int, u64p, vp]
         L.rsx_split_pass_to.restype = C.c_int
         L.rsx_split_pass_to.argtypes = [vp, sz, LP, u64p, C.c_int, u64p, vp]
+    L.rsx_multi_route.restype = C.c_int
+    L.rsx_multi_route.argtypes = [u64p, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(RsxRoute)]
+    L.rsx_multi_splitters.restype = C.c_int
+    L.rsx_multi_splitters.argtypes = [u64p, sz, C.c_int, u64p]
+    L.rsx_sort_shard.restype = C.c_int
+    L.rsx_sort_shard.argtypes = [C.POINTER(RsxComm), C.POINTER(RsxShardOps), vp, sz, vp, C.POINTER(vp), sz, LP, C.c_uint32,
+                                 C.POINTER(vp), C.POINTER(sz), C.POINTER(RsxMultiReport), vp]
+    L.rsx_sort_multi.restype = C.c_int
+    L.rsx_sort_multi.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp), C.POINTER(vp), C.POINTER(sz), sz, LP,
+                                 C.c_uint32, C.POINTER(vp), C.POINTER(sz), C.POINTER(RsxMultiReport)]
     L.rsx_workspace_bytes.restype = sz
     L.rsx_workspace_bytes.argtypes = [sz, LP, C.c_int]
     L.rsx_reserve.restype = C.c_int

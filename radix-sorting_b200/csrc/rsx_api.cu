@@ -301,8 +301,8 @@ struct Plan {
 	PassGeometry geo;
 	uint32_t tiles;
 	bool wide;
-	size_t status_bytes_per_col;
-	size_t off_status, off_rec[2], off_idx[2], total;
+	size_t status_bytes; // one look-back buffer: tiles x 256 status words
+	size_t off_status[2], off_head, off_rec[2], off_idx[2], total;
 	int n_rec_bufs;
 };
 
@@ -314,10 +314,14 @@ void make_plan(Plan &P, size_t n, const rsx_layout *L, const KeyDesc &kd, int ra
 	P.geo = scatter_geometry(P.rb, P.pl_bytes);
 	P.tiles = (uint32_t)((n + P.geo.tile - 1) / P.geo.tile);
 	P.wide = n >= (1ULL << 30) || g_force_wide.load(std::memory_order_relaxed);
-	P.status_bytes_per_col = (size_t)P.tiles * kBins * (P.wide ? 8 : 4);
-	size_t off = align_up(sizeof(WsHead), 256);
-	P.off_status = off;
-	off += align_up(P.status_bytes_per_col * kd.key_bytes, 256);
+	P.status_bytes = align_up((size_t)P.tiles * kBins * (P.wide ? 8 : 4), 256);
+	// [status 0 | WsHead | status 1 | rank-sort buffers]: status 0 and the head's zeroed part are
+	// adjacent, so ONE memset prepares a sort; status 1 is zeroed by the first live pass.
+	P.off_status[0] = 0;
+	P.off_head = P.status_bytes;
+	size_t off = P.off_head + align_up(sizeof(WsHead), 256);
+	P.off_status[1] = off;
+	off += P.status_bytes;
 	P.n_rec_bufs = 0;
 	P.off_rec[0] = P.off_rec[1] = P.off_idx[0] = P.off_idx[1] = 0;
 	if (rank_idx_bytes) {
@@ -338,17 +342,23 @@ void make_plan(Plan &P, size_t n, const rsx_layout *L, const KeyDesc &kd, int ra
 	P.total = off;
 }
 
-int run_scatter(const PassBuffers &pb, const Plan &P, int col, WsHead *ws, bool forced, void *status,
-                unsigned int *ticket, int num_sms, cudaStream_t st) {
-	CU(launch_scatter(pb, P.n, P.rb, P.pl_bytes, P.kd, col, ws, forced, status, ticket, P.wide, num_sms, st));
+int run_scatter(const PassBuffers &pb, const Plan &P, int col, unsigned char *wsp, bool forced, bool single,
+                int num_sms, cudaStream_t st) {
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
+	CU(launch_scatter(pb, P.n, P.rb, P.pl_bytes, P.kd, col, ws, forced, wsp + P.off_status[0],
+	                  single ? nullptr : wsp + P.off_status[1], &ws->tickets[col], P.wide, num_sms, st));
 	return RSX_OK;
+}
+
+// zero look-back buffer 0 + the head's counters: one memset
+cudaError_t zero_workspace(const Plan &P, unsigned char *wsp, cudaStream_t st) {
+	return cudaMemsetAsync(wsp, 0, P.off_head + kWsZeroBytes, st);
 }
 
 // Enqueue memset + K1 + K2 (+ passes).  Everything is asynchronous on `st`.
 int enqueue_front(const void *src, const Plan &P, unsigned char *wsp, int num_sms, cudaStream_t st) {
-	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
-	CU(cudaMemsetAsync(wsp, 0, kWsZeroBytes, st));
-	CU(cudaMemsetAsync(wsp + P.off_status, 0, P.status_bytes_per_col * P.kd.key_bytes, st));
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
+	CU(zero_workspace(P, wsp, st));
 	prof_mark(st, true);
 	CU(launch_histogram(src, P.n, P.rb, P.kd, ws, num_sms, st));
 	prof_mark(st);
@@ -358,10 +368,8 @@ int enqueue_front(const void *src, const Plan &P, unsigned char *wsp, int num_sm
 }
 
 int enqueue_passes(const PassBuffers &pb, const Plan &P, unsigned char *wsp, int num_sms, cudaStream_t st) {
-	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
 	for (uint32_t c = 0; c < P.kd.key_bytes; ++c) {
-		int r = run_scatter(pb, P, (int)c, ws, false, wsp + P.off_status + c * P.status_bytes_per_col,
-		                    &ws->tickets[c], num_sms, st);
+		int r = run_scatter(pb, P, (int)c, wsp, false, false, num_sms, st);
 		if (r)
 			return r;
 		prof_mark(st);
@@ -369,8 +377,8 @@ int enqueue_passes(const PassBuffers &pb, const Plan &P, unsigned char *wsp, int
 	return RSX_OK;
 }
 
-int read_ctl(Lease &L, cudaStream_t st, unsigned long long launches0, rsx_report *rep, bool staged) {
-	const WsHead *ws = static_cast<const WsHead *>(L.ptr);
+int read_ctl(Lease &L, size_t head_off, cudaStream_t st, unsigned long long launches0, rsx_report *rep, bool staged) {
+	const WsHead *ws = reinterpret_cast<const WsHead *>(static_cast<const unsigned char *>(L.ptr) + head_off);
 	Ctl *pinned = L.pinned;
 	CU(cudaMemcpyAsync(pinned, &ws->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
@@ -461,7 +469,7 @@ PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes) {
 }
 
 cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_bytes, int payload_bytes,
-                           const KeyDesc &kd, int col, const WsHead *ws, bool forced, void *status,
+                           const KeyDesc &kd, int col, const WsHead *ws, bool forced, void *status0, void *status1,
                            unsigned int *ticket, bool wide, int num_sms, cudaStream_t st,
                            const unsigned long long *dest_base, const unsigned char *owner,
                            const unsigned long long *splitters, int nsplit, int ndest) {
@@ -476,7 +484,8 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
 	sp.dd = make_digit_desc(kd, col);
 	sp.offs = ws->offs + (size_t)col * kBins;
 	sp.ctl = forced ? nullptr : &ws->ctl;
-	sp.status = status;
+	sp.status[0] = status0;
+	sp.status[1] = status1;
 	sp.ticket = ticket;
 	sp.pad_rec = pad_record(kd);
 	sp.dbg = nullptr;
@@ -642,7 +651,7 @@ static int sort_device(void *src, void *aux, size_t n, const rsx_layout *layout,
 		rsx_report local;
 		if (!rep)
 			rep = &local;
-		if ((r = read_ctl(L, st, l0, rep, staged)))
+		if ((r = read_ctl(L, 0, st, l0, rep, staged)))
 			return r;
 		*result = rep->result_in_aux ? aux : src;
 		return RSX_OK;
@@ -667,7 +676,7 @@ static int sort_device(void *src, void *aux, size_t n, const rsx_layout *layout,
 	rsx_report local;
 	if (!rep)
 		rep = &local;
-	if ((r = read_ctl(L, st, l0, rep, staged)))
+	if ((r = read_ctl(L, P.off_head, st, l0, rep, staged)))
 		return r;
 	*result = rep->result_in_aux ? aux : src;
 	return RSX_OK;
@@ -757,7 +766,7 @@ static int rank_device(const void *src, void *ib, size_t n, const rsx_layout *la
 		rsx_report local;
 		if (!rep)
 			rep = &local;
-		if ((r = read_ctl(L, st, l0, rep, staged)))
+		if ((r = read_ctl(L, 0, st, l0, rep, staged)))
 			return r;
 		*result = static_cast<unsigned char *>(ib) + (rep->result_in_aux ? n * (size_t)idx_bytes : 0);
 		return RSX_OK;
@@ -770,7 +779,7 @@ static int rank_device(const void *src, void *ib, size_t n, const rsx_layout *la
 		return r;
 	L.enqueued(st);
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
-	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
 	const int sms = g_dev[dev].num_sms;
 	if ((r = enqueue_front(src, P, wsp, sms, st)))
 		return r;
@@ -798,7 +807,7 @@ static int rank_device(const void *src, void *ib, size_t n, const rsx_layout *la
 	rsx_report local;
 	if (!rep)
 		rep = &local;
-	if ((r = read_ctl(L, st, l0, rep, staged)))
+	if ((r = read_ctl(L, P.off_head, st, l0, rep, staged)))
 		return r;
 	*result = rep->result_in_aux ? ibb + n * (size_t)idx_bytes : ibb; // radix_sort_rank.hpp:91
 	return RSX_OK;
@@ -901,13 +910,13 @@ int rsx_histogram(const void *src, size_t n, const rsx_layout *layout, uint64_t 
 		return r;
 	L.enqueued(st);
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
-	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
 	if ((r = enqueue_front(src, P, wsp, g_dev[dev].num_sms, st)))
 		return r;
 	rsx_report local;
 	if (!rep)
 		rep = &local;
-	if ((r = read_ctl(L, st, l0, rep, false)))
+	if ((r = read_ctl(L, P.off_head, st, l0, rep, false)))
 		return r;
 	rep->live_mask = L.pinned->live_mask; // report the probe even when the input is presorted
 	rep->ncols = L.pinned->ncols;
@@ -941,7 +950,7 @@ int rsx_scatter_pass(const void *src, void *dst, const void *payload_src, void *
 		return r;
 	L.enqueued(st);
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
-	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
 	const int sms = g_dev[dev].num_sms;
 	if ((r = enqueue_front(src, P, wsp, sms, st))) // histogram + scan give this column's offsets
 		return r;
@@ -952,7 +961,7 @@ int rsx_scatter_pass(const void *src, void *dst, const void *payload_src, void *
 	pb.pl_first = payload_src;
 	pb.pl_buf[0] = payload_dst;
 	pb.pl_buf[1] = payload_dst;
-	if ((r = run_scatter(pb, P, col, ws, true, wsp + P.off_status, &ws->tickets[col], sms, st)))
+	if ((r = run_scatter(pb, P, col, wsp, true, true, sms, st)))
 		return r;
 	CU(cudaStreamSynchronize(st));
 	L.drained();
@@ -981,15 +990,16 @@ int rsx_scatter_pass_to(const void *src, size_t n, const rsx_layout *layout, int
 		return r;
 	L.enqueued(st);
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
-	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
 	const int sms = g_dev[dev].num_sms;
-	if ((r = enqueue_front(src, P, wsp, sms, st)))
-		return r;
+	// no histogram needed: destinations get explicit base addresses; only the look-back state and
+	// the tile ticket have to be zero (the caller already histogrammed this shard to route it)
+	CU(zero_workspace(P, wsp, st));
 	CU(cudaMemcpyAsync(ws->dest_base, dest_base, sizeof(uint64_t) * ndest, cudaMemcpyHostToDevice, st));
 	CU(cudaMemcpyAsync(ws->owner, owner, kBins, cudaMemcpyHostToDevice, st));
 	PassBuffers pb{};
 	pb.rec_first = src;
-	CU(launch_scatter(pb, P.n, P.rb, 0, P.kd, col, ws, true, wsp + P.off_status, &ws->tickets[col], P.wide, sms, st,
+	CU(launch_scatter(pb, P.n, P.rb, 0, P.kd, col, ws, true, wsp + P.off_status[0], nullptr, &ws->tickets[col], P.wide, sms, st,
 	                  ws->dest_base, ws->owner, nullptr, 0, ndest));
 	CU(cudaStreamSynchronize(st));
 	L.drained();
@@ -1056,12 +1066,11 @@ int rsx_split_pass_to(const void *src, size_t n, const rsx_layout *layout, const
 		return r;
 	L.enqueued(st);
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
-	WsHead *ws = reinterpret_cast<WsHead *>(wsp);
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
 	const int sms = g_dev[dev].num_sms;
 	// no histogram needed: destinations get explicit base addresses; only the look-back state and
 	// the tile ticket have to be zero
-	CU(cudaMemsetAsync(wsp, 0, kWsZeroBytes, st));
-	CU(cudaMemsetAsync(wsp + P.off_status, 0, P.status_bytes_per_col, st));
+	CU(zero_workspace(P, wsp, st));
 	unsigned char owner[kBins];
 	for (int b = 0; b < kBins; ++b)
 		owner[b] = (unsigned char)(b <= nsplit ? b : nsplit); // "digit" == destination
@@ -1069,7 +1078,7 @@ int rsx_split_pass_to(const void *src, size_t n, const rsx_layout *layout, const
 	CU(cudaMemcpyAsync(ws->owner, owner, kBins, cudaMemcpyHostToDevice, st));
 	PassBuffers pb{};
 	pb.rec_first = src;
-	CU(launch_scatter(pb, P.n, P.rb, 0, P.kd, 0, ws, true, wsp + P.off_status, &ws->tickets[0], P.wide, sms, st,
+	CU(launch_scatter(pb, P.n, P.rb, 0, P.kd, 0, ws, true, wsp + P.off_status[0], nullptr, &ws->tickets[0], P.wide, sms, st,
 	                  ws->dest_base, ws->owner, reinterpret_cast<const unsigned long long *>(splitters), nsplit, nsplit + 1));
 	CU(cudaStreamSynchronize(st));
 	L.drained();

@@ -1,163 +1,40 @@
-"""Single-box multi-GPU partitioned radix sort (BASELINE config 5).
+"""Single-box multi-GPU partitioned radix sort (BASELINE config 5) -- the Python
+launcher side.
 
-One process per GPU (torchrun), `torch.distributed` for the plumbing.  The reference has no
-multi-device path; this is the MSD-then-LSD composition of its own primitives:
+The algorithm and its host orchestration live in C++ inside librsx.so (csrc/rsx_multi.cu,
+`rsx_sort_shard` in include/rsx.h): histogram -> all-gather of the digit counts -> routing of the
+top live digit's buckets (or of key ranges for skewed keys) -> fused partition + exchange into the
+owners' receive buffers over NVLink (or local partition + all-to-all) -> local LSD sort.  The
+concatenation of the ranks' outputs in rank order is bit-identical to `radix_sort` of the
+concatenated input.
 
-  1. every rank runs the fused histogram kernel (K1) on its shard -> per-column digit counts
-  2. all_gather of the (columns x 256) counts (a few KiB): global histogram, live columns,
-     and -- because every rank sees every rank's counts -- exact send/receive sizes
-  3. the highest globally-live column is the routing digit; its 256 buckets are assigned to
-     ranks as contiguous ranges balancing the global counts
-  4. one stable scatter pass (K3) on that column groups each rank's shard by bucket, hence by
-     destination rank
-  5. exchange.  Fused form (default): step 4's kernel stores every bucket straight into its
-     owner's receive buffer -- peer memory mapped with torch symmetric memory, written over
-     NVLink -- so the all-to-all costs no extra HBM pass (rsx_scatter_pass_to).  Baseline form
-     (fused=False, or when symmetric memory is unavailable): all_to_all_single over NCCL with
-     the exact split sizes.  Either way a receive buffer holds the chunks in source-rank
-     order, which keeps the global order stable
-  6. local LSD radix sort (K1-K3, device-side column skipping) of what was received
+This module only supplies what a one-process-per-GPU launcher (torchrun) has and a C library has
+not: the process group.  It wraps `torch.distributed` all-gather / barrier / all-to-all as the
+`rsx_comm` callbacks, allocates the peer-mapped receive buffer with torch symmetric memory, and
+calls `rsx_sort_shard`.  (A single process that owns all GPUs calls `rsx_sort_multi` instead, see
+tools/radix_multi_b200.cpp.)
 
-The concatenation of the ranks' outputs in rank order is the globally sorted sequence, and it
-is bit-identical to `radix_sort` of the concatenated input (tests/test_dist.py checks this
-with a two-process gloo group on CPU, using an oracle-backed engine supplied by the test).
-
-The local work goes through an *engine* object so that the host logic above can be tested
-without a GPU; the default engine is the CUDA library and raises if it is unavailable (there is
-no CPU fallback in the product).
+tests/test_dist.py runs the same C++ orchestration on CPU over gloo by passing oracle-backed local
+primitives (`rsx_shard_ops`); the product path always uses the library's CUDA kernels (ops=None)
+and fails without a GPU.
 """
 from __future__ import annotations
 
+import ctypes as C
 import importlib
-import time
-from dataclasses import dataclass
-from typing import List, Optional
+from dataclasses import dataclass, field
+from typing import Optional
 
 import numpy as np
 
 
-class CudaEngine:
-    """Local primitives on the GPU through librsx.so."""
-
-    def __init__(self):
-        self.rsx = importlib.import_module("radix-sorting_b200")
-        import torch
-        if not torch.cuda.is_available():
-            raise RuntimeError("CudaEngine needs a CUDA device; there is no CPU fallback")
-        self.torch = torch
-
-    def histogram(self, keys, kf) -> np.ndarray:
-        L = kf.layout(keys.element_size())
-        n = keys.numel() * keys.element_size() // L.record_bytes
-        if n < 2:  # the kernel needs n >= 2 (like the reference, which returns before counting)
-            h = np.zeros((L.key_bytes, 256), dtype=np.uint64)
-            if n == 1:
-                k = derive_key_py(bytes(keys.view(self.torch.uint8).cpu().numpy().tobytes()), L)
-                for c in range(L.key_bytes):
-                    h[c, (k >> (8 * c)) & 0xFF] = 1
-            return h
-        hist, _, _ = self.rsx.histogram(keys, kf)
-        return hist
-
-    def scatter_pass(self, src, dst, col, kf):
-        if src.numel():
-            self.rsx.scatter_pass(src, dst, col, kf)
-        return dst
-
-    def sort(self, src, aux, kf):
-        return self.rsx.radix_sort(src, aux, None, kf)
-
-    # ---- fused partition + exchange over peer memory (NVLink) ----------------------------------
-    _symm = {}  # (dtype, device) -> (tensor, handle): symmetric receive buffer, grown on demand
-    symm_error = None
-
-    def symmetric_recv(self, capacity, like, group):
-        """A receive buffer of >= capacity elements allocated symmetrically on every rank, with the
-        peers' addresses.  Returns (tensor, [base address per rank], handle) or None if symmetric
-        memory is not available here (the caller then uses the NCCL all-to-all)."""
-        try:
-            import torch.distributed._symmetric_memory as symm_mem
-        except Exception:
-            return None
-        import torch.distributed as dist
-        key = (like.dtype, like.device.index)
-        if key in self._symm and self._symm[key] is None:
-            return None  # failed before: do not retry on every call
-        cur = self._symm.get(key)
-        if cur is None or cur[0].numel() < capacity:
-            try:
-                t = symm_mem.empty(int(capacity * 1.02) + 1024, dtype=like.dtype, device=like.device)
-                h = symm_mem.rendezvous(t, group=group if group is not None else dist.group.WORLD)
-                cur = (t, h)
-            except Exception as e:  # no fabric / P2P support
-                self._symm[key] = None
-                CudaEngine.symm_error = repr(e)
-                return None
-            self._symm[key] = cur
-        t, h = cur
-        return t, [int(p) for p in h.buffer_ptrs], h
-
-    def scatter_pass_to(self, src, col, owner, dest_base, kf):
-        self.rsx.scatter_pass_to(src, col, owner, dest_base, kf)
-
-    # ---- key-range routing (skewed inputs) -------------------------------------------------------
-    def sample_keys(self, keys, kf, count) -> np.ndarray:
-        """`count` evenly spaced records' DERIVED keys (uint64)."""
-        L = kf.layout(keys.element_size())
-        n = keys.numel() * keys.element_size() // L.record_bytes
-        raw = keys.view(self.torch.uint8).view(n, L.record_bytes)
-        c = min(count, n)
-        idx = (self.torch.arange(c, device=keys.device, dtype=self.torch.int64) * n) // c  # exact integer stride
-        return derive_np(raw[idx].cpu().numpy(), L)
-
-    def split_counts(self, keys, splitters, kf):
-        return self.rsx.split_counts(keys, splitters, kf)
-
-    def split_pass_to(self, keys, splitters, dest_base, kf):
-        self.rsx.split_pass_to(keys, splitters, dest_base, kf)
-
-    def split_partition(self, keys, splitters, counts, kf):
-        """Local stable partition by key range (the non-fused form): returns the grouped copy."""
-        L = kf.layout(keys.element_size())
-        part = self.empty(keys.numel(), keys)
-        base, acc = [], 0
-        for c in counts:
-            base.append(part.data_ptr() + acc * L.record_bytes)
-            acc += c
-        self.rsx.split_pass_to(keys, splitters, base, kf)
-        return part
-
-    def empty(self, n, like):
-        return self.torch.empty(n, dtype=like.dtype, device=like.device)
-
-    _scratch = {}
-
-    def scratch(self, n, like):
-        """Grow-only cached buffer (the local sort's aux): no allocator traffic in steady state.
-        Like the receive buffer it is owned by the engine and reused by the next call."""
-        key = (like.dtype, like.device.index)
-        cur = self._scratch.get(key)
-        if cur is None or cur.numel() < n:
-            cur = None
-            self._scratch[key] = None
-            cur = self.torch.empty(int(n * 1.05) + 1024, dtype=like.dtype, device=like.device)
-            self._scratch[key] = cur
-        return cur[:n]
-
-
-def derive_key_py(record: bytes, L) -> int:
-    """Derived key of ONE record (radix_sort_basic_kdf.hpp:19-46) -- used for 1-element shards only."""
-    k = int.from_bytes(record[L.key_offset:L.key_offset + L.key_bytes], "little")
-    m, top = (1 << (8 * L.key_bytes)) - 1, 1 << (8 * L.key_bytes - 1)
-    if L.kdf_kind == 1:
-        k ^= top
-    elif L.kdf_kind == 2:
-        k ^= m if k & top else top
-    return (~k & m) if (L.flags & 1) else k
+def _rsx():
+    return importlib.import_module("radix-sorting_b200")
 
 
 def derive_np(records: np.ndarray, L) -> np.ndarray:
-    """Vectorised derived keys (uint64) of an (n, record_bytes) uint8 array."""
+    """Vectorised derived keys (uint64) of an (n, record_bytes) uint8 array
+    (radix_sort_basic_kdf.hpp:19-46); used by tests to predict key-range destinations."""
     kb = L.key_bytes
     k = np.zeros(records.shape[0], dtype=np.uint64)
     for b in range(kb):
@@ -174,196 +51,195 @@ def derive_np(records: np.ndarray, L) -> np.ndarray:
 
 
 def choose_splitters(samples: np.ndarray, world: int):
-    """world - 1 ascending derived-key splitters at the quantiles of the pooled samples."""
-    srt = np.sort(samples.astype(np.uint64))
-    return [int(srt[min(len(srt) - 1, (i * len(srt)) // world)]) for i in range(1, world)]
+    """world - 1 ascending derived-key splitters at the quantiles of the pooled samples
+    (rsx_multi_splitters)."""
+    s = np.ascontiguousarray(samples, dtype=np.uint64)
+    out = (C.c_uint64 * (world - 1))()
+    st = _rsx().lib().rsx_multi_splitters(s.ctypes.data_as(C.POINTER(C.c_uint64)), s.shape[0], world, out)
+    assert st == 0
+    return [int(x) for x in out]
 
 
 def assign_buckets(global_counts: np.ndarray, world: int) -> np.ndarray:
-    """Contiguous bucket ranges per rank, balancing counts: owner[b] = rank that receives
-    bucket b.  Greedy sweep against the ideal cumulative share; deterministic on every rank."""
-    total = int(global_counts.sum())
-    owner = np.zeros(256, dtype=np.int64)
-    if total == 0 or world == 1:
-        return owner
-    cum = np.cumsum(global_counts.astype(np.float64))
-    start = cum - global_counts  # exclusive prefix
-    mid = start + global_counts / 2.0  # a bucket goes to the rank whose share contains its midpoint
-    owner = np.minimum((mid * world / total).astype(np.int64), world - 1)
-    return np.maximum.accumulate(owner)  # monotone (contiguous ranges)
+    """Contiguous bucket ranges per rank balancing the counts: owner[b] = rank that receives
+    bucket b (the routing table of rsx_multi_route for a one-column histogram)."""
+    rsx = _rsx()
+    hist = np.zeros((world, 1, 256), dtype=np.uint64)
+    hist[0, 0] = np.asarray(global_counts, dtype=np.uint64)
+    route = rsx.RsxRoute()
+    st = rsx.lib().rsx_multi_route(hist.ctypes.data_as(C.POINTER(C.c_uint64)), world, 1, 0, 1e30, C.byref(route))
+    assert st == 0
+    return np.array(list(route.owner), dtype=np.int64)
 
 
 @dataclass
 class PartitionInfo:
-    routing_column: Optional[int]
-    live_columns: List[int]
-    send_counts: List[int]
-    recv_counts: List[int]
+    routing_column: Optional[int]  # None: nothing routed, -1: key-range routing
     n_out: int
     n_total: int
     imbalance: float
-    seconds: dict
+    fused: bool
+    seconds: dict = field(default_factory=dict)
 
 
-def _sort_by_key_ranges(keys, kf, L, group, engine, world, rank, dev, live, n_total, n_local, rec_elems, fused,
-                        sec, tick, t):
+class _Buffers:
+    """Grow-only work buffers per (device, dtype): the peer-mapped receive buffer (torch symmetric
+    memory), a plain receive buffer for the all-to-all exchange, and -- when the caller's tensor has
+    no slack -- a source copy with capacity."""
+    symm = {}   # key -> (tensor, handle), or None once symmetric memory turned out to be unavailable
+    plain = {}
+    src = {}
+    symm_error = None
+
+
+def _symmetric_recv(capacity_elems, like, group):
+    """(tensor, [peer base addresses], handle) of >= capacity elements, or None where symmetric
+    memory is unavailable (the exchange then goes through all_to_all_single)."""
+    import torch.distributed as dist
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+    except Exception as e:  # noqa: BLE001
+        _Buffers.symm_error = repr(e)
+        return None
+    key = (like.dtype, like.device.index)
+    if key in _Buffers.symm and _Buffers.symm[key] is None:
+        return None  # failed before: do not retry on every call
+    cur = _Buffers.symm.get(key)
+    if cur is None or cur[0].numel() < capacity_elems:
+        try:
+            t = symm_mem.empty(int(capacity_elems), dtype=like.dtype, device=like.device)
+            h = symm_mem.rendezvous(t, group=group if group is not None else dist.group.WORLD)
+            cur = (t, h)
+        except Exception as e:  # noqa: BLE001  (no fabric / P2P support)
+            _Buffers.symm[key] = None
+            _Buffers.symm_error = repr(e)
+            return None
+        _Buffers.symm[key] = cur
+    t, h = cur
+    return t, [int(p) for p in h.buffer_ptrs], h
+
+
+def partitioned_sort(keys, kf, group=None, n: Optional[int] = None, ops=None, fused: bool = True,
+                     key_range: bool = True):
+    """Globally sorts the concatenation (in rank order) of every rank's first `n` records of `keys`
+    (default: all of it).  Returns (this rank's slice of the sorted sequence, PartitionInfo).
+    `keys` is clobbered; tensor capacity beyond `n` is used as working space (a tensor without
+    slack costs one extra copy).  Collective: every rank of `group` must call it."""
     import torch
     import torch.distributed as dist
-    samples = engine.sample_keys(keys, kf, 8192) if n_local else np.zeros(0, dtype=np.uint64)
-    pad = np.full(8192, np.iinfo(np.uint64).max, dtype=np.uint64)  # ragged shards: fixed-size exchange
-    pad[: len(samples)] = samples
-    mine = torch.from_numpy(np.concatenate([[len(samples)], pad.view(np.int64)]).astype(np.int64)).to(dev)
-    gathered = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine, group=group)
-    pooled = np.concatenate([g.cpu().numpy()[1:1 + int(g[0])].view(np.uint64) for g in gathered])
-    splitters = choose_splitters(pooled, world)
-    counts = engine.split_counts(keys, splitters, kf) if n_local else [0] * world
-    cmine = torch.tensor(counts, dtype=torch.int64, device=dev)
-    call = [torch.empty_like(cmine) for _ in range(world)]
-    dist.all_gather(call, cmine, group=group)
-    cnt = torch.stack(call).cpu().numpy()  # [source][destination]
-    send = [int(c) for c in cnt[rank]]
-    recv = [int(c) for c in cnt[:, rank]]
-    n_out = sum(recv)
-    t = tick("sample+split_counts", t)
-    symm = None
-    if fused and hasattr(engine, "symmetric_recv"):
-        cap = int(cnt.sum(axis=0).max()) * rec_elems
-        symm = engine.symmetric_recv(max(cap, 1), keys, group)
-        ok = torch.tensor([1 if symm is not None else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if not int(ok.item()):
-            symm = None
-    if symm is not None:
-        out_buf, bases, handle = symm
-        dest_base = [bases[d] + int(cnt[:rank, d].sum()) * L.record_bytes for d in range(world)]
-        handle.barrier()
-        if n_local:
-            engine.split_pass_to(keys, splitters, dest_base, kf)
-        torch.cuda.synchronize(dev)
-        handle.barrier()
-        t = tick("fused_partition_exchange", t)
-    else:
-        part = engine.split_partition(keys, splitters, counts, kf) if n_local else keys
-        t = tick("partition_pass", t)
-        out_buf = engine.empty(max(n_out, 1) * rec_elems, keys)
-        dist.all_to_all_single(out_buf[: n_out * rec_elems], part, [r * rec_elems for r in recv],
-                               [s * rec_elems for s in send], group=group)
-        t = tick("all_to_all", t)
-        del part
-    recv_view = out_buf[: n_out * rec_elems]
-    if n_out > 1:
-        aux = keys if keys.numel() >= recv_view.numel() else (
-            engine.scratch(recv_view.numel(), keys) if hasattr(engine, "scratch") else engine.empty(recv_view.numel(), keys))
-        res = engine.sort(recv_view, aux[: recv_view.numel()], kf)
-    else:
-        res = recv_view
-    t = tick("local_sort", t)
-    sec["exchange"] = ("fused peer stores (NVLink)" if symm is not None else "all_to_all_single") + ", key-range routing"
-    info = PartitionInfo(-1, live, send, recv, n_out, n_total, n_out / max(n_total / world, 1), sec)
-    return res, info
-
-
-def partitioned_sort(keys, kf, group=None, engine=None, timers: bool = False, fused: bool = True,
-                     skew_threshold: float = 1.15):
-    """Globally sorts the concatenation (in rank order) of every rank's `keys`.
-    Returns (this rank's slice of the sorted sequence, PartitionInfo).  `keys` is clobbered."""
-    import torch
-    import torch.distributed as dist
-    engine = engine or CudaEngine()
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
+    rsx = _rsx()
+    lib = rsx.lib()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = keys.device
-    sec = {}
-
-    def tick(name, t0):
-        if timers:
-            if dev.type == "cuda":
-                torch.cuda.synchronize(dev)
-            sec[name] = time.perf_counter() - t0
-        return time.perf_counter()
-
-    t = time.perf_counter()
+    on_gpu = dev.type == "cuda"
+    if on_gpu and ops is not None:
+        raise ValueError("local primitives may only be substituted on CPU (tests)")
+    if not on_gpu and ops is None:
+        raise RuntimeError("the partitioned sort runs on CUDA devices; there is no CPU path")
     L = kf.layout(keys.element_size())
-    cols = L.key_bytes
-    n_local = keys.numel() * keys.element_size() // L.record_bytes
+    rb = L.record_bytes
+    esz = keys.element_size()
+    rec_elems = rb // esz
+    count = keys.numel() // rec_elems
+    n = count if n is None else n
+    stream = torch.cuda.current_stream(dev).cuda_stream if on_gpu else 0
+    coll_dev = dev if on_gpu else torch.device("cpu")
 
-    # 1-2. histograms of every rank, visible to every rank
-    hist = engine.histogram(keys, kf)  # (cols, 256) uint64, digits of the DERIVED key
-    mine = torch.from_numpy(hist.astype(np.int64).reshape(-1)).to(dev)
-    gathered = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine, group=group)
-    per_rank = torch.stack(gathered).cpu().numpy().reshape(world, cols, 256)  # [source rank][column][bucket]
-    total = per_rank.sum(axis=0)
-    n_total = int(total[0].sum())
-    t = tick("histogram+allgather", t)
+    # ---- the launcher's collectives as rsx_comm callbacks ------------------------------------------
+    state = {"handle": None, "src": None, "recv": None, "err": None}
 
-    # 3. routing digit = highest column that is not constant over ALL ranks (device-side column
-    #    skipping, lifted to the global level)
-    live = [c for c in range(cols) if int(total[c].max()) != n_total]
-    if not live or world == 1:
-        out = engine.sort(keys, engine.empty(keys.numel(), keys), kf) if n_local > 1 else keys
-        info = PartitionInfo(None, live, [n_local], [n_local], n_local, n_total, 1.0, sec)
-        return out, info
-    top = live[-1]
-    owner = assign_buckets(total[top], world)
-    rec_elems = L.record_bytes // keys.element_size()
-    predicted = max(int(total[top][owner == d].sum()) for d in range(world)) / max(n_total / world, 1)
-    if predicted > skew_threshold and hasattr(engine, "split_counts") and world - 1 <= 15:
-        # Skewed routing digit (e.g. zipf: most of the mass in one top bucket): bucket-granular
-        # ranges cannot balance, so route by key range instead -- splitters at the quantiles of a
-        # pooled sample (sample sort); exact per-destination counts from one counting pass.
-        return _sort_by_key_ranges(keys, kf, L, group, engine, world, rank, dev, live, n_total, n_local,
-                                   rec_elems, fused, sec, tick, t)
-    send = [int(per_rank[rank, top, owner == d].sum()) for d in range(world)]
-    recv = [int(per_rank[s, top, owner == rank].sum()) for s in range(world)]
-    n_out = sum(recv)
+    def cb_allgather(ctx, send, recv, nbytes):
+        try:
+            mine = torch.from_numpy(np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), shape=(nbytes,)).copy())
+            mine = mine.to(coll_dev)
+            out = torch.empty(world * nbytes, dtype=torch.uint8, device=coll_dev)
+            dist.all_gather_into_tensor(out, mine, group=group)
+            np.ctypeslib.as_array(C.cast(recv, C.POINTER(C.c_uint8)), shape=(world * nbytes,))[:] = out.cpu().numpy()
+            return 0
+        except Exception as e:  # noqa: BLE001
+            state["err"] = e
+            return rsx.RSX_ERR_CUDA
 
-    symm = None
-    if fused and hasattr(engine, "symmetric_recv"):
-        # every rank must take the same branch: capacity is the global maximum, known to all
-        cap = max(int(per_rank[:, top, owner == d].sum()) for d in range(world)) * rec_elems
-        symm = engine.symmetric_recv(max(cap, 1), keys, group)
-        ok = torch.tensor([1 if symm is not None else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if not int(ok.item()):
-            symm = None
-    if symm is not None:
-        # 4+5 fused: the stable pass on the routing column stores every destination's records
-        # straight into that rank's receive buffer (peer memory over NVLink), one contiguous run
-        # per (tile, destination).  Layout of a receive buffer: chunks in source-rank order.
-        out_buf, bases, handle = symm
-        dest_base = [bases[d] + int(per_rank[:rank, top, owner == d].sum()) * L.record_bytes for d in range(world)]
-        handle.barrier()  # nobody is still sorting out of its receive buffer from the previous call
-        if n_local:
-            engine.scatter_pass_to(keys, top, owner, dest_base, kf)
-        torch.cuda.synchronize(dev)
-        handle.barrier()  # all remote stores have landed
-        t = tick("fused_partition_exchange", t)
-    else:
-        # 4. group the shard by routing bucket (stable): destinations become contiguous ranges
-        part = engine.empty(keys.numel(), keys)
-        engine.scatter_pass(keys, part, top, kf)
-        t = tick("partition_pass", t)
-        # 5. exchange
-        out_buf = engine.empty(max(n_out, 1) * rec_elems, keys)
-        dist.all_to_all_single(out_buf[: n_out * rec_elems], part, [r * rec_elems for r in recv],
-                               [s * rec_elems for s in send], group=group)
-        t = tick("all_to_all", t)
-        del part
+    def cb_barrier(ctx):
+        try:
+            if on_gpu:
+                torch.cuda.synchronize(dev)
+            if state["handle"] is not None:
+                state["handle"].barrier()
+            else:
+                dist.barrier(group=group)
+            return 0
+        except Exception as e:  # noqa: BLE001
+            state["err"] = e
+            return rsx.RSX_ERR_CUDA
 
-    # 6. local LSD sort of the received records (chunks arrive in source-rank order: stable)
-    recv_view = out_buf[: n_out * rec_elems]
-    if n_out > 1:
-        aux = keys if keys.numel() >= recv_view.numel() else (
-            engine.scratch(recv_view.numel(), keys) if hasattr(engine, "scratch") else engine.empty(recv_view.numel(), keys))
-        res = engine.sort(recv_view, aux[: recv_view.numel()], kf)
-    else:
-        res = recv_view
-    t = tick("local_sort", t)
-    sec["exchange"] = "fused peer stores (NVLink)" if symm is not None else "NCCL all_to_all_single"
-    info = PartitionInfo(top, live, send, recv, n_out, n_total, n_out / max(n_total / world, 1), sec)
-    return res, info
+    def cb_alltoallv(ctx, send, sbytes, recv, rbytes):
+        try:
+            by_ptr = {state["src"].data_ptr(): state["src"], state["recv"].data_ptr(): state["recv"]}
+            s_t, r_t = by_ptr[send].view(torch.uint8), by_ptr[recv].view(torch.uint8)
+            ss, rs = [int(sbytes[d]) for d in range(world)], [int(rbytes[d]) for d in range(world)]
+            dist.all_to_all_single(r_t[: sum(rs)], s_t[: sum(ss)], rs, ss, group=group)
+            return 0
+        except Exception as e:  # noqa: BLE001
+            state["err"] = e
+            return rsx.RSX_ERR_CUDA
+
+    comm = rsx.RsxComm(rank, world, rsx.ALLGATHER_FN(cb_allgather), rsx.BARRIER_FN(cb_barrier),
+                       rsx.ALLTOALLV_FN(cb_alltoallv), None)
+    flags = (0 if key_range else rsx.MULTI_NO_KEY_RANGE)
+
+    capacity = count  # records the caller's tensor can hold
+    src = keys
+    rep = rsx.RsxMultiReport()
+    for attempt in range(2):
+        cap_elems = capacity * rec_elems
+        symm = _symmetric_recv(cap_elems, keys, group) if (fused and on_gpu) else None
+        if fused and on_gpu:  # every rank must take the same branch
+            ok = torch.tensor([1 if symm is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if not int(ok.item()):
+                symm = None
+        if symm is not None:
+            recv, bases, handle = symm
+            peers = (C.c_void_p * world)(*bases)
+            state["handle"] = handle
+        else:
+            key = (keys.dtype, dev.index if on_gpu else -1)
+            cur = _Buffers.plain.get(key)
+            if cur is None or cur.numel() < cap_elems:
+                cur = torch.empty(cap_elems, dtype=keys.dtype, device=dev)
+                _Buffers.plain[key] = cur
+            recv, peers, state["handle"] = cur, None, None
+        state["src"], state["recv"] = src, recv
+        res_ptr, n_out = C.c_void_p(), C.c_size_t(0)
+        st = lib.rsx_sort_shard(C.byref(comm), C.byref(ops) if ops is not None else None, src.data_ptr(), n, recv.data_ptr(), peers, capacity, C.byref(L),
+                                flags | (0 if symm is not None else rsx.MULTI_NO_FUSED), C.byref(res_ptr), C.byref(n_out),
+                                C.byref(rep), stream)
+        if st == rsx.RSX_ERR_WORKSPACE and attempt == 0:
+            # the routed sizes need more room than the tensors have (same verdict on every rank,
+            # nothing was moved yet): grow once, with some slack for the next calls
+            capacity = int(rep.needed_capacity * 1.03) + 1024
+            skey = (keys.dtype, dev.index if on_gpu else -1)
+            cur = _Buffers.src.get(skey)
+            if cur is None or cur.numel() < capacity * rec_elems:
+                cur = torch.empty(capacity * rec_elems, dtype=keys.dtype, device=dev)
+                _Buffers.src[skey] = cur
+            cur[: n * rec_elems].copy_(keys.view(-1)[: n * rec_elems])
+            src = cur
+            continue
+        if state["err"] is not None:
+            raise state["err"]
+        if st != rsx.RSX_OK:
+            raise rsx.RsxError(st, "rsx_sort_shard")
+        break
+    out_t = src if res_ptr.value == src.data_ptr() else recv
+    res = out_t.view(-1)[: n_out.value * rec_elems]
+    routing = None if (rep.routing_column < 0 and not rep.key_range) else (-1 if rep.key_range else int(rep.routing_column))
+    sec = {"histogram+allgather": rep.seconds_histogram, "routing": rep.seconds_routing,
+           "partition+exchange": rep.seconds_exchange, "local_sort": rep.seconds_local_sort,
+           "exchange": ("fused peer stores (NVLink)" if rep.fused else "all_to_all_single") +
+                       (", key-range routing" if rep.key_range else "")}
+    return res, PartitionInfo(routing, int(n_out.value), int(rep.n_total), float(rep.imbalance), bool(rep.fused), sec)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -379,12 +255,13 @@ def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world
     rsx.fill_keys(pristine, seed=2, start=rank * n_per_gpu, dist=dname, mask=mask, orv=orv)
     _, s0, x0 = rsx.verify(pristine, kf)
     chk0 = torch.tensor([s0 & 0x7FFFFFFFFFFFFFFF, x0 & 0x7FFFFFFFFFFFFFFF, n_per_gpu], dtype=torch.int64, device=dev)
-    engine = CudaEngine()
-    keys = torch.empty_like(pristine)
+    fused = not getattr(args, "no_fused", False)
+    # working tensor with slack: the routed shard sizes differ a little from n_per_gpu
+    keys = torch.empty(int(n_per_gpu * 1.04) + 4096, dtype=tdt, device=dev)
     times, last = [], None
     launches0 = 0
     for it in range(args.warmup + args.steps):
-        keys.copy_(pristine)
+        keys[:n_per_gpu].copy_(pristine)
         if it == args.warmup:
             launches0 = rsx.total_kernel_launches()
             if sampler is not None:
@@ -393,7 +270,7 @@ def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        res, info = partitioned_sort(keys, kf, engine=engine, fused=not getattr(args, "no_fused", False))
+        res, info = partitioned_sort(keys, kf, n=n_per_gpu, fused=fused)
         e1.record()
         e1.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -432,10 +309,7 @@ def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world
         xor0 ^= int(a[1])
         xor1 ^= int(b[1])
     verified = bool(ok_sorted.item()) and n_in == sum(n_outs) and boundaries_ok and sum_ok and xor0 == xor1
-    # one extra pass with host timers for the phase breakdown (not part of the timed steps)
-    keys.copy_(pristine)
-    dist.barrier()
-    _, info_t = partitioned_sort(keys, kf, engine=engine, timers=True, fused=not getattr(args, "no_fused", False))
+    info_t = info  # rsx_sort_shard reports its own per-phase host-clock seconds
     # e2e: every rank's shard starts and ends in pinned HOST memory (H2D + global sort + D2H timed)
     e2e = None
     if not getattr(args, "no_e2e", False):
@@ -455,8 +329,8 @@ def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world
                 dist.barrier()
                 torch.cuda.synchronize(dev)
                 t0 = time.perf_counter()
-                keys.copy_(h_in, non_blocking=True)
-                r_e, info_e = partitioned_sort(keys, kf, engine=engine, fused=not getattr(args, "no_fused", False))
+                keys[:n_per_gpu].copy_(h_in, non_blocking=True)
+                r_e, info_e = partitioned_sort(keys, kf, n=n_per_gpu, fused=fused)
                 h_out[: info_e.n_out].copy_(r_e.view(-1)[: info_e.n_out], non_blocking=True)
                 torch.cuda.synchronize(dev)
                 dt = torch.tensor([time.perf_counter() - t0], device=dev)
@@ -484,7 +358,8 @@ def bench_partitioned(args, rsx, tname, n_per_gpu, dname, mask, orv, rank, world
                    "imbalance_max_over_mean": max(n_outs) / (n_total / world), "verified": verified,
                    "timing": "CUDA events per rank around partitioned_sort, all_reduce MAX over ranks, mean of steps",
                    "l2": "inputs larger than L2, restored before every step",
-                   "phase_seconds_rank0": info_t.seconds, "symm_error": CudaEngine.symm_error,
+                   "phase_seconds_rank0": info_t.seconds, "symm_error": _Buffers.symm_error,
+                   "host_orchestration": "C++ rsx_sort_shard (csrc/rsx_multi.cu) with torch.distributed callbacks",
                    "ms_steps": [round(x, 3) for x in times]},
         "roofline": {"bound": "hbm", "kernel": "whole partitioned sort, per GPU", "achieved": moved / (ms_per_step * 1e-3) / 1e9,
                      "peak": None, "unit": "GB/s", "frac": None, "traffic": None,

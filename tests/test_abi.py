@@ -79,24 +79,25 @@ def test_product_does_not_touch_the_oracle():
 
 
 def test_workspace_sizing_and_options_need_no_device(rsx):
-    """rsx_workspace_bytes is pure host arithmetic: a fixed head plus, per key column,
-    one 256-word look-back row per tile of the SMALLEST tile any kernel runs with."""
+    """rsx_workspace_bytes is pure host arithmetic: a fixed head plus TWO look-back
+    buffers (a pass works in one and re-zeroes the other for its successor), each one 256-word row
+    per tile of the SMALLEST tile any kernel of that record size runs with -- independent of the
+    number of key columns."""
     L = rsx.lib()
     L.rsx_workspace_bytes.restype = C.c_size_t
     L.rsx_workspace_bytes.argtypes = [C.c_size_t, C.c_void_p, C.c_int]
     u32, u64 = rsx.RsxLayout(4, 0, 4, 0, 0), rsx.RsxLayout(8, 0, 8, 0, 0)
     n = 1_000_000_000
     head = L.rsx_workspace_bytes(2, C.byref(u32), 0)
-    tiles = -(-n // 10240)
     w32 = L.rsx_workspace_bytes(n, C.byref(u32), 0)
-    assert 0 < w32 - tiles * 256 * 4 * 4 <= head + 4096            # 4 columns, 4-byte status words (n < 2^30)
+    assert 0 < w32 - 2 * -(-n // 10240) * 256 * 4 <= head + 4096   # 10 240-record tiles, 4-byte status words (n < 2^30)
     w64 = L.rsx_workspace_bytes(n, C.byref(u64), 0)
-    assert 0 < w64 - tiles * 256 * 4 * 8 <= head + 4096            # 8 columns
+    assert 0 < w64 - 2 * -(-n // 8192) * 256 * 4 <= head + 4096    # 8 192-record tiles; 8 columns cost no more than 4
     wide = L.rsx_workspace_bytes(1 << 30, C.byref(u32), 0)         # n >= 2^30: 8-byte status words
-    assert wide > 2 * w32
+    assert wide > 2 * w32 - head
     # rank sort: two record buffers beside the indices, nothing extra for 4/8-byte index types
     wr = L.rsx_workspace_bytes(n, C.byref(u32), 4)
-    assert wr >= w32 + 2 * n * 4 and wr - w32 - 2 * n * 4 < 4096
+    assert wr >= w32 + 2 * n * 4 and wr - 2 * n * 4 < 2 * w32  # (key + index tiles are smaller: more look-back rows)
     assert L.rsx_workspace_bytes(n, C.byref(u32), 2) >= wr + 2 * n * 4  # narrow index types sort through u32 lanes
     bad = rsx.RsxLayout(3, 0, 1, 0, 0)
     assert L.rsx_workspace_bytes(n, C.byref(bad), 0) == 0

@@ -1,6 +1,8 @@
-"""Multi-process host logic of the partitioned sort (radix-sorting_b200/dist.py), world_size 2
-and 3 over gloo on CPU.  The local primitives come from an oracle-backed engine defined HERE
-(tests may use the oracle; the product's default engine is CUDA-only)."""
+"""Multi-process run of the partitioned sort's host orchestration -- the C++ `rsx_sort_shard` of
+csrc/rsx_multi.cu, driven through radix-sorting_b200/dist.py -- at world_size 2 and 3 over gloo on
+CPU.  The local primitives are oracle-backed callbacks defined HERE (`rsx_shard_ops`; tests may use
+the oracle, the product's primitives are the CUDA kernels) and the exchange is gloo's
+all_to_all."""
 import importlib
 import os
 import sys
@@ -17,61 +19,78 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
-class OracleEngine:
-    """CPU stand-in for CudaEngine: same four primitives, computed by the oracle / numpy."""
+def make_oracle_ops(tname):
+    """rsx_shard_ops backed by the CPU oracle / numpy: lets the C++ orchestration of the partitioned
+    sort (csrc/rsx_multi.cu, rsx_sort_shard) run on host memory over gloo.  Test infrastructure:
+    the product always passes ops = NULL (the CUDA kernels)."""
+    import ctypes as C
+    import pyoracle
+    rsx = importlib.import_module("radix-sorting_b200")
+    dsort = importlib.import_module("radix-sorting_b200.dist")
+    orc = pyoracle.Oracle()
+    t = pyoracle.TYPES[tname]
+    L = t.layout()
 
-    def __init__(self, tname):
-        import pyoracle
-        self.orc = pyoracle.Oracle()
-        self.t = pyoracle.TYPES[tname]
+    def view(ptr, n):
+        if n == 0:
+            return np.zeros(0, dtype=t.dtype)
+        raw = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * t.record_bytes,))
+        return raw.view(t.dtype)
 
-    def _np(self, x):
-        return x.numpy().view(self.t.dtype)
+    def derived(a):
+        return dsort.derive_np(np.ascontiguousarray(a).view(np.uint8).reshape(a.shape[0], t.record_bytes), L)
 
-    def histogram(self, keys, kf):
-        _, rep, hist = self.orc.radix_sort(self._np(keys), self.t.layout(), want_hist=True)
-        if keys.numel() == 1:
-            k = self.orc.kdf(self._np(keys)[:1], self.t.layout())
-            for c in range(self.t.key_bytes):
-                hist[c, (k >> (8 * c)) & 0xFF] = 1
-        return hist
+    def hist(ctx, src, n, lay, out, stream):
+        h = np.zeros((t.key_bytes, 256), dtype=np.uint64)
+        d = derived(view(src, n))
+        for c in range(t.key_bytes):
+            h[c] = np.bincount(((d >> np.uint64(8 * c)) & np.uint64(0xFF)).astype(np.int64), minlength=256)
+        np.ctypeslib.as_array(out, shape=(t.key_bytes * 256,))[:] = h.reshape(-1)
+        return 0
 
-    def scatter_pass(self, src, dst, col, kf):
-        a = self._np(src)
-        L = self.t.layout()
-        digits = np.array([(self.orc.kdf(a[i:i + 1], L) >> (8 * col)) & 0xFF for i in range(a.shape[0])], dtype=np.int64)
-        dst.copy_(src[torch.from_numpy(np.argsort(digits, kind="stable"))])
-        return dst
+    def sample(ctx, src, n, lay, count, out, stream):
+        d = derived(view(src, n))
+        stride = n // count
+        np.ctypeslib.as_array(out, shape=(count,))[:] = d[np.arange(count) * stride]
+        return 0
 
-    def sort(self, src, aux, kf):
-        out, _, _ = self.orc.radix_sort(self._np(src), self.t.layout())
-        src.copy_(torch.from_numpy(out.view(src.numpy().dtype)))
-        return src
+    def dest_of(a, col, owner, split, nsplit):
+        d = derived(a)
+        if col >= 0:
+            own = np.ctypeslib.as_array(owner, shape=(256,)).astype(np.int64)
+            return own[((d >> np.uint64(8 * col)) & np.uint64(0xFF)).astype(np.int64)]
+        sp = np.ctypeslib.as_array(split, shape=(nsplit,)).copy()
+        return np.searchsorted(sp, d, side="right")
 
-    def empty(self, n, like):
-        return torch.empty(n, dtype=like.dtype)
+    def split_counts(ctx, src, n, lay, split, nsplit, counts, stream):
+        dest = dest_of(view(src, n), -1, None, split, nsplit)
+        np.ctypeslib.as_array(counts, shape=(nsplit + 1,))[:] = np.bincount(dest, minlength=nsplit + 1)
+        return 0
 
-    # key-range routing (skewed inputs)
-    def _derived(self, keys):
-        dsort = importlib.import_module("radix-sorting_b200.dist")
-        a = self._np(keys)
-        return dsort.derive_np(a.view(np.uint8).reshape(a.shape[0], self.t.record_bytes), self.t.layout())
+    def partition_to(ctx, src, n, lay, col, owner, split, nsplit, dest_base, ndest, stream):
+        a = view(src, n).copy()
+        dest = dest_of(a, col, owner, split, nsplit)
+        for d in range(ndest):
+            part = np.ascontiguousarray(a[dest == d])  # stable: input order inside a destination
+            if part.shape[0]:
+                C.memmove(int(dest_base[d]), part.ctypes.data, part.nbytes)
+        return 0
 
-    def sample_keys(self, keys, kf, count):
-        d = self._derived(keys)
-        idx = np.linspace(0, len(d) - 1, num=min(count, len(d))).astype(np.int64)
-        return d[idx]
+    def sort(ctx, src, aux, n, lay, result, stream):
+        a = view(src, n)
+        out, _, _ = orc.radix_sort(a, L)
+        a[:] = out
+        result[0] = src
+        return 0
 
-    def split_counts(self, keys, splitters, kf):
-        dest = np.searchsorted(np.array(splitters, dtype=np.uint64), self._derived(keys), side="right")
-        return [int((dest == j).sum()) for j in range(len(splitters) + 1)]
-
-    def split_partition(self, keys, splitters, counts, kf):
-        dest = np.searchsorted(np.array(splitters, dtype=np.uint64), self._derived(keys), side="right")
-        return keys[torch.from_numpy(np.argsort(dest, kind="stable"))].clone()
+    ops = rsx.RsxShardOps(rsx.OPS_HIST_FN(hist), rsx.OPS_SAMPLE_FN(sample), rsx.OPS_SPLIT_COUNTS_FN(split_counts),
+                          rsx.OPS_PARTITION_FN(partition_to), rsx.OPS_SORT_FN(sort), None)
+    return ops
 
 
 def _worker(rank, world, port, tname, n_per, dist_name, mask, q):
+    import faulthandler
+    faulthandler.dump_traceback_later(45, exit=True)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -88,7 +107,8 @@ def _worker(rank, world, port, tname, n_per, dist_name, mask, q):
         tdt = {4: torch.int32, 8: torch.int64}[t.key_bytes]
         keys = torch.from_numpy(allkeys[lo:hi].view(np.int32 if t.key_bytes == 4 else np.int64).copy())
         kf = rsx.KeyFunc(t.kdf_kind, False, t.record_bytes, t.key_offset, t.key_bytes)
-        res, info = dsort.partitioned_sort(keys, kf, engine=OracleEngine(tname))
+        ops = make_oracle_ops(tname)
+        res, info = dsort.partitioned_sort(keys, kf, ops=ops, fused=False)
         q.put((rank, res.numpy().tobytes(), info.n_out, info.routing_column, info.imbalance))
     finally:
         dist.destroy_process_group()
@@ -103,7 +123,7 @@ def _run(world, tname, bounds, dist_name="uniform", mask=(1 << 64) - 1):
     procs = [ctx.Process(target=_worker, args=(r, world, port, tname, bounds, dist_name, mask, q)) for r in range(world)]
     for p in procs:
         p.start()
-    outs = sorted(q.get(timeout=180) for _ in range(world))
+    outs = sorted(q.get(timeout=60) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
