@@ -100,6 +100,13 @@ int rsx_histogram(const void *src, size_t n, const rsx_layout *layout,
                   uint64_t *hist_out /* key_bytes*256 */, uint64_t *descents_out,
                   rsx_report *report, void *stream);
 
+/* The 256-bin histogram of ONE column of the derived key (one shared-memory atomic per record
+ * instead of key_bytes: the kernel then runs at HBM speed).  The multi-GPU sort routes on the top
+ * column and does not need the others.  `src` device, `hist_out` host (256 entries).  Float keys:
+ * top column only (a lower column's digit depends on the sign bit in the top byte). */
+int rsx_histogram_column(const void *src, size_t n, const rsx_layout *layout, int col,
+                         uint64_t *hist_out /* 256 */, void *stream);
+
 /* One stable 8-bit-digit scatter pass (radix_sort.hpp:83-88) on column `col`, device
  * pointers only, unconditionally (no column skipping).  payload_* may be NULL; otherwise a
  * payload_bytes (4 or 8) lane is carried with the records. */
@@ -169,6 +176,8 @@ typedef struct rsx_shard_ops {
 	                    const uint64_t *splitters, int nsplit, const uint64_t *dest_base, int ndest, void *stream);
 	int (*sort)(void *ctx, void *src, void *aux, size_t n, const rsx_layout *L, void **result, void *stream);
 	void *ctx;
+	/* optional: histogram of one column only (NULL: the orchestration always uses `hist`) */
+	int (*hist_column)(void *ctx, const void *src, size_t n, const rsx_layout *L, int col, uint64_t *hist256, void *stream);
 } rsx_shard_ops;
 
 /* Routing decision, a pure function of the all-gathered histograms (identical on every rank). */
@@ -199,6 +208,7 @@ typedef struct rsx_multi_report {
 
 #define RSX_MULTI_NO_FUSED 1u     /* exchange through comm->alltoallv instead of peer stores */
 #define RSX_MULTI_NO_KEY_RANGE 2u /* always route by bucket ranges (tests)                  */
+#define RSX_MULTI_FULL_HISTOGRAM 4u /* count every column for routing, not just the top one (tests) */
 
 int rsx_multi_route(const uint64_t *hist_all /* [world][cols][256] */, int world, int cols, int rank,
                     double skew_threshold, rsx_route *out);

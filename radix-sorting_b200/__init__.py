@@ -35,7 +35,7 @@ RSX_ERR_WORKSPACE, RSX_ERR_IDX_RANGE, RSX_ERR_MIXED_MEMORY = -4, -5, -6
 
 #: every symbol include/rsx.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "rsx_sort", "rsx_sort_rank", "rsx_histogram", "rsx_scatter_pass", "rsx_scatter_pass_to",
+    "rsx_sort", "rsx_sort_rank", "rsx_histogram", "rsx_histogram_column", "rsx_scatter_pass", "rsx_scatter_pass_to",
     "rsx_split_counts", "rsx_split_pass_to",
     "rsx_multi_route", "rsx_multi_splitters", "rsx_sort_shard", "rsx_sort_multi",
     "rsx_workspace_bytes",
@@ -59,7 +59,7 @@ class RsxReport(C.Structure):
 
 
 RSX_MAX_RANKS = 16
-MULTI_NO_FUSED, MULTI_NO_KEY_RANGE = 1, 2
+MULTI_NO_FUSED, MULTI_NO_KEY_RANGE, MULTI_FULL_HISTOGRAM = 1, 2, 4
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
 BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
@@ -79,13 +79,15 @@ OPS_SPLIT_COUNTS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, _
                                   C.POINTER(C.c_uint64), C.c_void_p)
 OPS_PARTITION_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, _LP, C.c_int, C.POINTER(C.c_uint8),
                                C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_uint64), C.c_int, C.c_void_p)
+OPS_HIST_COLUMN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, _LP, C.c_int, C.POINTER(C.c_uint64), C.c_void_p)
 OPS_SORT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, _LP, C.POINTER(C.c_void_p), C.c_void_p)
 
 
 class RsxShardOps(C.Structure):
     """struct rsx_shard_ops: local primitives (NULL pointer = the library's CUDA kernels)."""
     _fields_ = [("hist", OPS_HIST_FN), ("sample", OPS_SAMPLE_FN), ("split_counts", OPS_SPLIT_COUNTS_FN),
-                ("partition_to", OPS_PARTITION_FN), ("sort", OPS_SORT_FN), ("ctx", C.c_void_p)]
+                ("partition_to", OPS_PARTITION_FN), ("sort", OPS_SORT_FN), ("ctx", C.c_void_p),
+                ("hist_column", OPS_HIST_COLUMN_FN)]
 
 
 class RsxRoute(C.Structure):
@@ -133,6 +135,8 @@ def _lib() -> C.CDLL:
     L.rsx_sort_rank.argtypes = [vp, vp, sz, LP, C.c_int, C.POINTER(vp), RP, vp]
     L.rsx_histogram.restype = C.c_int
     L.rsx_histogram.argtypes = [vp, sz, LP, u64p, u64p, RP, vp]
+    L.rsx_histogram_column.restype = C.c_int
+    L.rsx_histogram_column.argtypes = [vp, sz, LP, C.c_int, u64p, vp]
     L.rsx_scatter_pass.restype = C.c_int
     L.rsx_scatter_pass.argtypes = [vp, vp, vp, vp, C.c_int, sz, LP, C.c_int, vp]
     if hasattr(L, "rsx_scatter_pass_to"):

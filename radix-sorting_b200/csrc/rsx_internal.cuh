@@ -80,12 +80,11 @@ cudaError_t launch_histogram(const void *src, size_t n, uint32_t record_bytes, c
 cudaError_t launch_setup(const void *src, size_t n, uint32_t record_bytes, const KeyDesc &kd,
                          WsHead *ws, cudaStream_t st);
 
-// status0 / status1: look-back words, tiles * 256 entries of 4 (n < 2^30) or 8 bytes each; a pass
-// works in status[ordinal & 1] and re-zeroes the other one (status1 may be null: single pass).
+// status: look-back words for this column, tiles * 256 entries of 4 (n < 2^30) or 8 bytes, zeroed.
 // ctl == nullptr: forced pass (ordinal 0, never skipped) for rsx_scatter_pass.
 cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_bytes, int payload_bytes,
                            const KeyDesc &kd, int col, const WsHead *ws_offsets /*offs + ctl*/,
-                           bool forced, void *status0, void *status1, unsigned int *ticket, bool wide_offsets,
+                           bool forced, void *status, unsigned int *ticket, bool wide_offsets,
                            int num_sms, cudaStream_t st, const unsigned long long *dest_base = nullptr,
                            const unsigned char *owner = nullptr, const unsigned long long *splitters = nullptr,
                            int nsplit = 0, int ndest = 0);

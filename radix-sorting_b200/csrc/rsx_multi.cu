@@ -108,7 +108,14 @@ int cuda_sort(void *, void *src, void *aux, size_t n, const rsx_layout *L, void 
 	return rsx_sort(src, aux, n, L, result, nullptr, stream);
 }
 
-const rsx_shard_ops kCudaOps = {cuda_hist, cuda_sample, cuda_split_counts, cuda_partition_to, cuda_sort, nullptr};
+int cuda_hist_column(void *, const void *src, size_t n, const rsx_layout *L, int col, uint64_t *hist, void *stream) {
+	memset(hist, 0, sizeof(uint64_t) * 256);
+	if (n == 0)
+		return RSX_OK;
+	return rsx_histogram_column(src, n, L, col, hist, stream);
+}
+
+const rsx_shard_ops kCudaOps = {cuda_hist, cuda_sample, cuda_split_counts, cuda_partition_to, cuda_sort, nullptr, cuda_hist_column};
 
 } // namespace
 
@@ -218,26 +225,66 @@ int rsx_sort_shard(const rsx_comm *comm, const rsx_shard_ops *ops_in, void *src,
 	int r;
 	auto t0 = clk::now();
 
-	// 1-2. histograms of every rank, visible to every rank
-	const size_t hwords = (size_t)cols * 256;
+	// 1-2. histograms of every rank, visible to every rank.  Routing only needs the TOP column, and
+	// counting one column runs at HBM speed (one atomic per record instead of key_bytes), so that
+	// is tried first; only when the top column is constant over all ranks (keys with constant high
+	// bytes) every column is counted to find the highest live one.
 	// (the all-gather also carries every rank's buffer capacity: the too-small verdict below must
 	// be the same on every rank even when the ranks' buffers differ)
-	std::vector<uint64_t> hist(hwords + 1), gathered((hwords + 1) * world), hist_all(hwords * world);
-	if ((r = ops.hist(octx, src, n, L, hist.data(), stream)))
-		return r;
-	hist[hwords] = capacity;
-	if ((r = comm->allgather(comm->ctx, hist.data(), gathered.data(), (hwords + 1) * sizeof(uint64_t))))
-		return r;
+	const size_t hwords = (size_t)cols * 256;
+	std::vector<uint64_t> hist_all(hwords * world, 0);
 	uint64_t min_capacity = ~0ULL;
-	for (int g = 0; g < world; ++g) {
-		memcpy(&hist_all[(size_t)g * hwords], &gathered[(size_t)g * (hwords + 1)], hwords * sizeof(uint64_t));
-		min_capacity = std::min(min_capacity, gathered[(size_t)g * (hwords + 1) + hwords]);
+	bool have_route_hist = false;
+	if (ops.hist_column && cols > 1 && !(flags & RSX_MULTI_FULL_HISTOGRAM)) {
+		std::vector<uint64_t> h(256 + 1), g((256 + 1) * (size_t)world);
+		if ((r = ops.hist_column(octx, src, n, L, cols - 1, h.data(), stream)))
+			return r;
+		h[256] = capacity;
+		if ((r = comm->allgather(comm->ctx, h.data(), g.data(), h.size() * sizeof(uint64_t))))
+			return r;
+		uint64_t tot[256] = {}, n_total = 0, mx = 0;
+		for (int gq = 0; gq < world; ++gq) {
+			for (int b = 0; b < 256; ++b)
+				tot[b] += g[(size_t)gq * 257 + b];
+			min_capacity = std::min(min_capacity, g[(size_t)gq * 257 + 256]);
+		}
+		for (int b = 0; b < 256; ++b) {
+			n_total += tot[b];
+			mx = std::max(mx, tot[b]);
+		}
+		if (mx != n_total) { // the top column is live: it is the routing digit
+			have_route_hist = true;
+			for (int gq = 0; gq < world; ++gq) {
+				uint64_t *dst = &hist_all[(size_t)gq * hwords];
+				const uint64_t *top = &g[(size_t)gq * 257];
+				uint64_t s = 0;
+				for (int b = 0; b < 256; ++b) {
+					dst[(size_t)(cols - 1) * 256 + b] = top[b];
+					s += top[b];
+				}
+				for (int c = 0; c + 1 < cols; ++c) // unknown columns: any two buckets, "not constant"
+					dst[(size_t)c * 256] = s - s / 2, dst[(size_t)c * 256 + 1] = s / 2;
+			}
+		}
+	}
+	if (!have_route_hist) {
+		std::vector<uint64_t> hist(hwords + 1), gathered((hwords + 1) * world);
+		if ((r = ops.hist(octx, src, n, L, hist.data(), stream)))
+			return r;
+		hist[hwords] = capacity;
+		if ((r = comm->allgather(comm->ctx, hist.data(), gathered.data(), (hwords + 1) * sizeof(uint64_t))))
+			return r;
+		min_capacity = ~0ULL;
+		for (int g = 0; g < world; ++g) {
+			memcpy(&hist_all[(size_t)g * hwords], &gathered[(size_t)g * (hwords + 1)], hwords * sizeof(uint64_t));
+			min_capacity = std::min(min_capacity, gathered[(size_t)g * (hwords + 1) + hwords]);
+		}
 	}
 	rsx_route route;
 	const double thr = (flags & RSX_MULTI_NO_KEY_RANGE) ? 1e30 : 1.15;
 	if ((r = rsx_multi_route(hist_all.data(), world, cols, rank, thr, &route)))
 		return r;
-	rep->live_mask = route.live_mask;
+	rep->live_mask = have_route_hist ? (1u << (cols - 1)) : route.live_mask; // top-column shortcut: only that column is known
 	rep->n_total = route.n_total;
 	rep->seconds_histogram = since(t0);
 	t0 = clk::now();

@@ -51,10 +51,7 @@ struct ScatterParams {
 	DigitDesc dd;
 	const unsigned long long *offs; // this column's exclusive scan (256 entries)
 	const Ctl *ctl;                 // nullptr: forced pass
-	// Look-back state, OffT[num_tiles][256] each.  The pass with live ordinal j works in status[j & 1]
-	// and re-zeroes the rows of status[(j + 1) & 1] for the pass after it (whose previous user, pass
-	// j - 1, has completed): one memset per sort instead of one buffer per column.
-	void *status[2];
+	void *status;                   // OffT[num_tiles][256], zeroed by the host (one buffer per column)
 	unsigned int *ticket;
 	ulonglong2 pad_rec;             // record whose derived key is all ones (tail padding)
 	unsigned long long *dbg;        // RSX_PHASE_TIMING builds only: per-phase cycle accumulators
@@ -318,8 +315,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 	const uint32_t lt = lanemask_lt();
 	const DigitDesc dd = p.dd;
 	uint32_t *wh = s_wh + warp * kBins;
-	OffT *status = static_cast<OffT *>(p.status[ord & 1]);
-	OffT *status_next = last ? nullptr : static_cast<OffT *>(p.status[(ord + 1) & 1]);
+	OffT *status = static_cast<OffT *>(p.status);
 	const R pad = make_pad<ES>(p.pad_rec);
 	const uint32_t full_tiles = (uint32_t)(p.n / TILE); // tiles [0, full_tiles) are complete
 	const uint32_t my_owner = (FUSED && tid < kBins) ? p.owner[tid] : 0u;
@@ -483,8 +479,6 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 			const uint32_t pad_digit = DM == DIGIT_SPLIT ? p.nsplit : (uint32_t)kBins - 1;
 			const uint32_t agg = (!full && tid == pad_digit) ? tcount - ((uint32_t)TILE - valid) : tcount;
 			st_status(&status[(size_t)tile * kBins + tid], (OffT)((tile == 0 ? SB::kPfx : SB::kAgg) | (OffT)agg));
-			if (status_next != nullptr)
-				status_next[(size_t)tile * kBins + tid] = 0; // the next live pass finds its look-back rows empty
 			// exclusive scan of tcount over the 256 digit threads (8 warps)
 			uint32_t x = tcount;
 #pragma unroll

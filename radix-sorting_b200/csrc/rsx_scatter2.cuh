@@ -152,8 +152,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter2_kerne
 	const uint32_t lt = lanemask_lt();
 	const DigitDesc dd = p.dd;
 	uint32_t *wh = s_wh + warp * kBins;
-	OffT *status = static_cast<OffT *>(p.status[ord & 1]);
-	OffT *status_next = last ? nullptr : static_cast<OffT *>(p.status[(ord + 1) & 1]);
+	OffT *status = static_cast<OffT *>(p.status);
 	const R pad = make_pad<ES>(p.pad_rec);
 	const uint32_t full_tiles = (uint32_t)(p.n / TILE); // tiles [0, full_tiles) are complete
 	const uint32_t t0 = warp * (ITEMS * 32) + lane;     // this thread's first record inside a tile
@@ -245,8 +244,6 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter2_kerne
 			// tail padding sorts last (after every real record of the last digit): not part of the aggregate
 			const uint32_t agg = (!full && tid == (uint32_t)kBins - 1) ? tcount - ((uint32_t)TILE - valid) : tcount;
 			st_status(&status[(size_t)tile * kBins + tid], (OffT)((tile == 0 ? SB::kPfx : SB::kAgg) | (OffT)agg));
-			if (status_next != nullptr)
-				status_next[(size_t)tile * kBins + tid] = 0; // the next live pass finds its look-back rows empty
 			uint32_t x = tcount;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1) {

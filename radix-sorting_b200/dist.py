@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import importlib
+import time
 from dataclasses import dataclass, field
 from typing import Optional
 

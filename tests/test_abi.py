@@ -79,10 +79,8 @@ def test_product_does_not_touch_the_oracle():
 
 
 def test_workspace_sizing_and_options_need_no_device(rsx):
-    """rsx_workspace_bytes is pure host arithmetic: a fixed head plus TWO look-back
-    buffers (a pass works in one and re-zeroes the other for its successor), each one 256-word row
-    per tile of the SMALLEST tile any kernel of that record size runs with -- independent of the
-    number of key columns."""
+    """rsx_workspace_bytes is pure host arithmetic: a fixed head plus, per key column,
+    one 256-word look-back row per tile of the SMALLEST tile any kernel of that record size runs with."""
     L = rsx.lib()
     L.rsx_workspace_bytes.restype = C.c_size_t
     L.rsx_workspace_bytes.argtypes = [C.c_size_t, C.c_void_p, C.c_int]
@@ -90,9 +88,9 @@ def test_workspace_sizing_and_options_need_no_device(rsx):
     n = 1_000_000_000
     head = L.rsx_workspace_bytes(2, C.byref(u32), 0)
     w32 = L.rsx_workspace_bytes(n, C.byref(u32), 0)
-    assert 0 < w32 - 2 * -(-n // 10240) * 256 * 4 <= head + 4096   # 10 240-record tiles, 4-byte status words (n < 2^30)
+    assert 0 < w32 - 4 * -(-n // 10240) * 256 * 4 <= head + 4096   # 4 columns x 10 240-record tiles, 4-byte status words
     w64 = L.rsx_workspace_bytes(n, C.byref(u64), 0)
-    assert 0 < w64 - 2 * -(-n // 8192) * 256 * 4 <= head + 4096    # 8 192-record tiles; 8 columns cost no more than 4
+    assert 0 < w64 - 8 * -(-n // 8192) * 256 * 4 <= head + 4096    # 8 columns x 8 192-record tiles
     wide = L.rsx_workspace_bytes(1 << 30, C.byref(u32), 0)         # n >= 2^30: 8-byte status words
     assert wide > 2 * w32 - head
     # rank sort: two record buffers beside the indices, nothing extra for 4/8-byte index types

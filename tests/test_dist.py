@@ -48,6 +48,12 @@ def make_oracle_ops(tname):
         np.ctypeslib.as_array(out, shape=(t.key_bytes * 256,))[:] = h.reshape(-1)
         return 0
 
+    def hist_column(ctx, src, n, lay, col, out, stream):
+        d = derived(view(src, n))
+        np.ctypeslib.as_array(out, shape=(256,))[:] = np.bincount(
+            ((d >> np.uint64(8 * col)) & np.uint64(0xFF)).astype(np.int64), minlength=256)
+        return 0
+
     def sample(ctx, src, n, lay, count, out, stream):
         d = derived(view(src, n))
         stride = n // count
@@ -84,7 +90,8 @@ def make_oracle_ops(tname):
         return 0
 
     ops = rsx.RsxShardOps(rsx.OPS_HIST_FN(hist), rsx.OPS_SAMPLE_FN(sample), rsx.OPS_SPLIT_COUNTS_FN(split_counts),
-                          rsx.OPS_PARTITION_FN(partition_to), rsx.OPS_SORT_FN(sort), None)
+                          rsx.OPS_PARTITION_FN(partition_to), rsx.OPS_SORT_FN(sort), None,
+                          rsx.OPS_HIST_COLUMN_FN(hist_column))
     return ops
 
 

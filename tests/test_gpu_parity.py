@@ -192,6 +192,30 @@ def test_histogram_kernel(rsx, torch, oracle, tname, n, dist, mask):
         assert rep.live_mask == sum(1 << orep.cols[i] for i in range(orep.ncols))
 
 
+@pytest.mark.parametrize("tname", ["u16", "u32", "u64", "i32", "i64", "f32", "f64", "rec8_u32", "rec16_u64", "rec16_f64"])
+def test_histogram_column_kernel(rsx, torch, oracle, tname):
+    """rsx_histogram_column: one column of the derived key's digit histogram (the multi-GPU routing
+    histogram) == that column of the oracle's full histogram; descending layouts too."""
+    import ctypes as C
+    t = TYPES[tname]
+    data = make_input(tname, 300001, 55, "and2")
+    src = to_dev(torch, data)
+    for desc in (False, True):
+        _, _, ohist = oracle.radix_sort(data, t.layout(descending=desc), want_hist=True)
+        L = rsx.RsxLayout(t.record_bytes, t.key_offset, t.key_bytes, t.kdf_kind, 1 if desc else 0)
+        cols = [t.key_bytes - 1] if t.kdf_kind == 2 else range(t.key_bytes)
+        for col in cols:
+            out = np.zeros(256, dtype=np.uint64)
+            st = rsx.lib().rsx_histogram_column(src.data_ptr(), 300001, C.byref(L), col,
+                                                out.ctypes.data_as(C.POINTER(C.c_uint64)), None)
+            assert st == 0
+            assert np.array_equal(out, ohist[col]), (tname, desc, col)
+    if t.kdf_kind == 2:  # a lower column of a float key needs the sign bit: rejected
+        out = np.zeros(256, dtype=np.uint64)
+        assert rsx.lib().rsx_histogram_column(src.data_ptr(), 300001, C.byref(L), 0,
+                                              out.ctypes.data_as(C.POINTER(C.c_uint64)), None) == rsx.RSX_ERR_INVALID
+
+
 @pytest.mark.parametrize("off", [1, 2, 3, 5])
 def test_unaligned_pointers(rsx, torch, oracle, off):
     """Buffers that are element-aligned but not 16-byte aligned (head/tail path of K1)."""

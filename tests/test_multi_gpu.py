@@ -131,7 +131,9 @@ def test_sort_multi_matches_oracle(rsx, oracle, tname, dist, mask):
     if dist == "zipf":
         assert reps[0].key_range == 1
     if dist == "uniform":
-        assert reps[0].fused == 1 and reps[0].routing_column == t.key_bytes - 1
+        assert reps[0].fused == 1
+        if mask == -1:
+            assert reps[0].routing_column == t.key_bytes - 1
 
 
 @pytest.mark.gpu
@@ -150,10 +152,15 @@ def test_torchrun_selftest_fused_and_nccl():
             "r = d.selftest(rsx, rank, dist.get_world_size(), dev, n_per=1 << 20)\n"
             "print('SELFTEST', json.dumps(r)) if rank == 0 else None\n"
             "dist.destroy_process_group()\n")
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ng}",
-                          "--master-addr", "127.0.0.1", "--master-port", "29611", "-c", code],
-                         capture_output=True, text=True, timeout=900)
-    if out.returncode != 0 and "-c" in out.stderr and "No such file" in out.stderr:
-        pytest.skip("torch.distributed.run cannot take -c here")
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix="_rsx_selftest.py", delete=False) as f:
+        f.write(code)
+        script = f.name
+    try:
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ng}",
+                              "--master-addr", "127.0.0.1", "--master-port", "29611", script],
+                             capture_output=True, text=True, timeout=900)
+    finally:
+        os.unlink(script)
     assert out.returncode == 0, out.stderr[-3000:]
     assert "SELFTEST" in out.stdout and '"passed": true' in out.stdout
