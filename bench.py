@@ -391,6 +391,77 @@ def bench_single(args, rsx, torch, workload, dev, steps, warmup, do_e2e, do_cpu)
     }
 
 
+def run_sweep(args):
+    """N2: the reference's Google-Benchmark sweep, n = 1 .. 40 M (x10) of uint32_t
+    keys for radix_sort, radix_sort_rank, std::sort and qsort (radix_bench.cpp:86-138) -- the device
+    path (device-resident buffers: CUDA-event time and wall clock of the synchronous call) with the
+    reference's CPU path and its two yardsticks timed beside it on one host core.  Input restored
+    before every iteration (the reference's loop does not, radix_bench.cpp:91-93).  One JSON line."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import pyoracle
+    rsx = importlib.import_module("radix-sorting_b200")
+    dev = torch.device("cuda", 0)
+    U = rsx.KeyFunc(rsx.KDF_UNSIGNED)
+    ref = None
+    if os.path.exists(pyoracle.LIB_REF):
+        ref = C.CDLL(pyoracle.LIB_REF)
+        ref.ref_time_u32.restype = C.c_double
+        ref.ref_time_u32.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    try:
+        os.sched_setaffinity(0, {sorted(os.sched_getaffinity(0))[0]})
+    except Exception:
+        pass
+    keygen = load_keygen()
+    rows = []
+    n = 1
+    while n <= 40_000_000:
+        pristine = torch.empty(n, dtype=torch.int32, device=dev)
+        rsx.fill_keys(pristine, seed=5)
+        src, aux = torch.empty_like(pristine), torch.empty_like(pristine)
+        ib = torch.empty(2 * n, dtype=torch.int32, device=dev)
+        row = {"n": n}
+        for name, fn in (("radix_sort", lambda: rsx.radix_sort(src, aux, None, U)),
+                         ("radix_sort_rank", lambda: rsx.radix_sort_rank(src, ib, n, U))):
+            ev, wall = [], []
+            for it in range(12):
+                src.copy_(pristine)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0 = time.perf_counter()
+                e0.record()
+                fn()
+                e1.record()
+                e1.synchronize()
+                t1 = time.perf_counter()
+                if it >= 2:
+                    ev.append(e0.elapsed_time(e1) * 1e-3)
+                    wall.append(t1 - t0)
+            row["gpu_" + name] = {"device_us": min(ev) * 1e6, "wall_us": min(wall) * 1e6, "KeyRate_Mkeys_s": n / min(wall) / 1e6}
+        if ref is not None:
+            h = keygen.fill(5, 0, n, 4).astype(np.uint32)
+            assert h[:1000].tobytes() == pristine[:1000].cpu().numpy().tobytes()
+            work, haux = np.empty_like(h), np.zeros(2 * n, dtype=np.uint32)
+            iters = 5 if n <= 1_000_000 else 2
+            for kind, name in enumerate(("radix_sort", "radix_sort_rank", "std_sort", "qsort")):
+                if kind == 3 and n > 10_000_000:
+                    iters = 1
+                sec = ref.ref_time_u32(kind, h.ctypes.data, work.ctypes.data, haux.ctypes.data, n, iters)
+                row["cpu_" + name] = {"wall_us": sec * 1e6, "KeyRate_Mkeys_s": n / sec / 1e6}
+            row["gpu_over_cpu_radix_sort"] = row["cpu_radix_sort"]["wall_us"] / row["gpu_radix_sort"]["wall_us"]
+        rows.append(row)
+        print(json.dumps(row), file=sys.stderr, flush=True)
+        del pristine, src, aux, ib
+        n *= 10 if n < 10_000_000 else 4
+    crossover = next((r["n"] for r in rows if r.get("gpu_over_cpu_radix_sort", 0) > 1.0), None)
+    print(json.dumps({"sweep": "radix_bench.cpp:86-138 on uint32_t keys", "rows": rows,
+                      "cpu": "oracle/_ref (unmodified reference headers + std::sort / qsort), 1 core" if ref else None,
+                      "device_path_faster_than_cpu_from_n": crossover,
+                      "note": "below the crossover the device path is launch-latency-bound and SLOWER than the "
+                              "reference on one CPU core; a drop-in caller should keep small arrays on the host"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -398,6 +469,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sweep", action="store_true", help="the reference's n = 1 .. 40 M sweep (radix_bench.cpp) with CPU columns")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (u64 / config 5 / zipf sub-lines)")
@@ -420,6 +492,9 @@ def main():
 
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+        return
+    if args.sweep:
+        run_sweep(args)
         return
 
     import torch

@@ -11,8 +11,12 @@
  * tests/golden/ref_outputs.npz, (3) serve as the `--impl reference` / cpu_baseline arm of
  * bench.py (cpu_baseline.kind = "reference").
  */
+#include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
 #include <type_traits>
 
 #include "radix_sort.hpp"      // reference: radix_sort.hpp:98-115
@@ -124,6 +128,37 @@ int ref_radix_sort_rank(int type_code, const void *src, void *index_buffer, size
                         int idx_bytes, int descending) {
 #define CALL_RANK(T) rank_idx<T>(src, index_buffer, n, idx_bytes, descending)
 	DISPATCH(type_code, CALL_RANK);
+}
+
+// The n-sweep of the reference's benchmark harness (radix_bench.cpp:86-138) for uint32_t keys, timed
+// in here so that tiny n is not dominated by FFI overhead: kind 0 = radix_sort, 1 = radix_sort_rank
+// (u32 indices), 2 = std::sort, 3 = qsort.  The input is restored from `pristine` before every
+// iteration OUTSIDE the timed region (the reference's own loop does not, radix_bench.cpp:91-93);
+// returns the best wall-clock seconds of `iters` runs (CLOCK_MONOTONIC_RAW, radix_experiment.cpp:203).
+static int cmp_u32(const void *a, const void *b) {
+	const uint32_t x = *static_cast<const uint32_t *>(a), y = *static_cast<const uint32_t *>(b);
+	return x < y ? -1 : (x > y ? 1 : 0);
+}
+double ref_time_u32(int kind, const uint32_t *pristine, uint32_t *work, uint32_t *aux /* 2n for kind 1 */, size_t n,
+                    int iters) {
+	double best = 1e300;
+	for (int it = 0; it < iters; ++it) {
+		memcpy(work, pristine, n * sizeof(uint32_t));
+		timespec t0, t1;
+		clock_gettime(CLOCK_MONOTONIC_RAW, &t0);
+		switch (kind) {
+		case 0: { volatile auto *r = radix_sort(work, aux, n); (void)r; break; }
+		case 1: { volatile auto *r = radix_sort_rank(work, aux, n); (void)r; break; }
+		case 2: std::sort(work, work + n); break;
+		case 3: qsort(work, n, sizeof(uint32_t), cmp_u32); break;
+		default: return -1.0;
+		}
+		clock_gettime(CLOCK_MONOTONIC_RAW, &t1);
+		const double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+		if (dt < best)
+			best = dt;
+	}
+	return best;
 }
 
 size_t ref_record_bytes(int type_code) {

@@ -223,7 +223,7 @@ int acquire(Lease &L, int dev, size_t bytes) {
 			D.ws_bytes = bytes;
 		}
 		if (!D.pinned)
-			CU(cudaHostAlloc((void **)&D.pinned, sizeof(Ctl), cudaHostAllocDefault));
+			CU(cudaHostAlloc((void **)&D.pinned, sizeof(Ctl), cudaHostAllocMapped));
 		D.busy = true;
 		L.ptr = D.ws;
 		L.pinned = D.pinned;
@@ -232,7 +232,7 @@ int acquire(Lease &L, int dev, size_t bytes) {
 	}
 	lk.unlock(); // another host thread is sorting on this device: private scratch for this call
 	CU(cudaMalloc(&L.ptr, bytes));
-	CU(cudaHostAlloc((void **)&L.pinned, sizeof(Ctl), cudaHostAllocDefault));
+	CU(cudaHostAlloc((void **)&L.pinned, sizeof(Ctl), cudaHostAllocMapped));
 	L.own_pinned = true;
 	return RSX_OK;
 }
@@ -356,13 +356,13 @@ cudaError_t zero_workspace(const Plan &P, unsigned char *wsp, cudaStream_t st) {
 }
 
 // Enqueue memset + K1 + K2 (+ passes).  Everything is asynchronous on `st`.
-int enqueue_front(const void *src, const Plan &P, unsigned char *wsp, int num_sms, cudaStream_t st) {
+int enqueue_front(const void *src, const Plan &P, unsigned char *wsp, Ctl *host_ctl, int num_sms, cudaStream_t st) {
 	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
 	CU(zero_workspace(P, wsp, st));
 	prof_mark(st, true);
 	CU(launch_histogram(src, P.n, P.rb, P.kd, ws, num_sms, st));
 	prof_mark(st);
-	CU(launch_setup(src, P.n, P.rb, P.kd, ws, st));
+	CU(launch_setup(src, P.n, P.rb, P.kd, ws, host_ctl, st));
 	prof_mark(st);
 	return RSX_OK;
 }
@@ -377,10 +377,11 @@ int enqueue_passes(const PassBuffers &pb, const Plan &P, unsigned char *wsp, int
 	return RSX_OK;
 }
 
-int read_ctl(Lease &L, size_t head_off, cudaStream_t st, unsigned long long launches0, rsx_report *rep, bool staged) {
-	const WsHead *ws = reinterpret_cast<const WsHead *>(static_cast<const unsigned char *>(L.ptr) + head_off);
+// The pass table (which buffer holds the result, radix_sort.hpp:89-92) reaches the host without a
+// copy: the setup kernel (or the single-CTA kernel) also stores it into the lease's mapped pinned
+// slot, so the host only has to wait for the stream.
+int read_ctl(Lease &L, cudaStream_t st, unsigned long long launches0, rsx_report *rep, bool staged) {
 	Ctl *pinned = L.pinned;
-	CU(cudaMemcpyAsync(pinned, &ws->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	L.drained();
 	prof_collect();
@@ -457,9 +458,9 @@ PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes) {
 	GEOV(4, 0, 1) GEOV(4, 0, 2) GEOV(4, 0, 3) GEOV(4, 0, 4) GEOV(4, 0, 5) GEOV(4, 0, 6) GEOV(4, 0, 7) GEOV(4, 0, 8) GEOV(4, 0, 9)
 	GEOV(8, 0, 1) GEOV(8, 0, 2) GEOV(8, 0, 3) GEOV(8, 0, 4) GEOV(8, 0, 5) GEOV(8, 0, 6) GEOV(8, 0, 7) GEOV(8, 0, 8) GEOV(8, 0, 9)
 	GEO2V(4, 0, 1) GEO2V(4, 0, 2) GEO2V(4, 0, 3) GEO2V(4, 0, 4) GEO2V(4, 0, 5) GEO2V(4, 0, 6) GEO2V(4, 0, 7) GEO2V(4, 0, 8) GEO2V(4, 0, 9)
-	GEO2V(4, 0, 10) GEO2V(4, 0, 11) GEO2V(4, 0, 12) GEO2V(4, 0, 13) GEO2V(4, 0, 14) GEO2V(4, 0, 15) GEO2V(4, 0, 16) GEO2V(4, 0, 17) GEO2V(4, 0, 18) GEO2V(4, 0, 19)
+	GEO2V(4, 0, 10) GEO2V(4, 0, 11) GEO2V(4, 0, 12) GEO2V(4, 0, 13) GEO2V(4, 0, 14) GEO2V(4, 0, 15) GEO2V(4, 0, 16) GEO2V(4, 0, 17) GEO2V(4, 0, 18) GEO2V(4, 0, 19) GEO2V(4, 0, 20) GEO2V(4, 0, 21) GEO2V(4, 0, 22) GEO2V(4, 0, 23)
 	GEO2V(8, 0, 1) GEO2V(8, 0, 2) GEO2V(8, 0, 3) GEO2V(8, 0, 4) GEO2V(8, 0, 5) GEO2V(8, 0, 6) GEO2V(8, 0, 7) GEO2V(8, 0, 8) GEO2V(8, 0, 9)
-	GEO2V(8, 0, 10) GEO2V(8, 0, 11) GEO2V(8, 0, 12) GEO2V(8, 0, 13) GEO2V(8, 0, 14) GEO2V(8, 0, 15) GEO2V(8, 0, 16) GEO2V(8, 0, 17) GEO2V(8, 0, 18) GEO2V(8, 0, 19)
+	GEO2V(8, 0, 10) GEO2V(8, 0, 11) GEO2V(8, 0, 12) GEO2V(8, 0, 13) GEO2V(8, 0, 14) GEO2V(8, 0, 15) GEO2V(8, 0, 16) GEO2V(8, 0, 17) GEO2V(8, 0, 18) GEO2V(8, 0, 19) GEO2V(8, 0, 20) GEO2V(8, 0, 21) GEO2V(8, 0, 22) GEO2V(8, 0, 23)
 #undef GEO2V
 #undef GEO
 #undef GEOV
@@ -643,14 +644,13 @@ static int sort_device(void *src, void *aux, size_t n, const rsx_layout *layout,
 		if (r)
 			return r;
 		L.enqueued(st);
-		WsHead *ws = static_cast<WsHead *>(L.ptr);
 		prof_mark(st, true);
-		CU(launch_small_sort(src, src, aux, nullptr, 0, n, layout->record_bytes, kd, &ws->ctl, st));
+		CU(launch_small_sort(src, src, aux, nullptr, 0, n, layout->record_bytes, kd, L.pinned, st));
 		prof_mark(st);
 		rsx_report local;
 		if (!rep)
 			rep = &local;
-		if ((r = read_ctl(L, 0, st, l0, rep, staged)))
+		if ((r = read_ctl(L, st, l0, rep, staged)))
 			return r;
 		*result = rep->result_in_aux ? aux : src;
 		return RSX_OK;
@@ -664,7 +664,7 @@ static int sort_device(void *src, void *aux, size_t n, const rsx_layout *layout,
 	L.enqueued(st);
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
 	const int sms = g_dev[dev].num_sms;
-	if ((r = enqueue_front(src, P, wsp, sms, st)))
+	if ((r = enqueue_front(src, P, wsp, L.pinned, sms, st)))
 		return r;
 	PassBuffers pb{};
 	pb.rec_first = src;
@@ -675,7 +675,7 @@ static int sort_device(void *src, void *aux, size_t n, const rsx_layout *layout,
 	rsx_report local;
 	if (!rep)
 		rep = &local;
-	if ((r = read_ctl(L, P.off_head, st, l0, rep, staged)))
+	if ((r = read_ctl(L, st, l0, rep, staged)))
 		return r;
 	*result = rep->result_in_aux ? aux : src;
 	return RSX_OK;
@@ -758,14 +758,13 @@ static int rank_device(const void *src, void *ib, size_t n, const rsx_layout *la
 		if (r)
 			return r;
 		L.enqueued(st);
-		WsHead *wsh = static_cast<WsHead *>(L.ptr);
 		prof_mark(st, true);
-		CU(launch_small_sort(src, nullptr, nullptr, ib, idx_bytes, n, layout->record_bytes, kd, &wsh->ctl, st));
+		CU(launch_small_sort(src, nullptr, nullptr, ib, idx_bytes, n, layout->record_bytes, kd, L.pinned, st));
 		prof_mark(st);
 		rsx_report local;
 		if (!rep)
 			rep = &local;
-		if ((r = read_ctl(L, 0, st, l0, rep, staged)))
+		if ((r = read_ctl(L, st, l0, rep, staged)))
 			return r;
 		*result = static_cast<unsigned char *>(ib) + (rep->result_in_aux ? n * (size_t)idx_bytes : 0);
 		return RSX_OK;
@@ -780,7 +779,7 @@ static int rank_device(const void *src, void *ib, size_t n, const rsx_layout *la
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
 	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
 	const int sms = g_dev[dev].num_sms;
-	if ((r = enqueue_front(src, P, wsp, sms, st)))
+	if ((r = enqueue_front(src, P, wsp, L.pinned, sms, st)))
 		return r;
 	CU(launch_iota_if_early(ib, idx_bytes, n, &ws->ctl, st)); // radix_sort_rank.hpp:52-57
 	unsigned char *ibb = static_cast<unsigned char *>(ib);
@@ -806,7 +805,7 @@ static int rank_device(const void *src, void *ib, size_t n, const rsx_layout *la
 	rsx_report local;
 	if (!rep)
 		rep = &local;
-	if ((r = read_ctl(L, P.off_head, st, l0, rep, staged)))
+	if ((r = read_ctl(L, st, l0, rep, staged)))
 		return r;
 	*result = rep->result_in_aux ? ibb + n * (size_t)idx_bytes : ibb; // radix_sort_rank.hpp:91
 	return RSX_OK;
@@ -910,12 +909,12 @@ int rsx_histogram(const void *src, size_t n, const rsx_layout *layout, uint64_t 
 	L.enqueued(st);
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
 	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
-	if ((r = enqueue_front(src, P, wsp, g_dev[dev].num_sms, st)))
+	if ((r = enqueue_front(src, P, wsp, L.pinned, g_dev[dev].num_sms, st)))
 		return r;
 	rsx_report local;
 	if (!rep)
 		rep = &local;
-	if ((r = read_ctl(L, P.off_head, st, l0, rep, false)))
+	if ((r = read_ctl(L, st, l0, rep, false)))
 		return r;
 	rep->live_mask = L.pinned->live_mask; // report the probe even when the input is presorted
 	rep->ncols = L.pinned->ncols;
@@ -996,7 +995,7 @@ int rsx_scatter_pass(const void *src, void *dst, const void *payload_src, void *
 	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
 	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
 	const int sms = g_dev[dev].num_sms;
-	if ((r = enqueue_front(src, P, wsp, sms, st))) // histogram + scan give this column's offsets
+	if ((r = enqueue_front(src, P, wsp, L.pinned, sms, st))) // histogram + scan give this column's offsets
 		return r;
 	PassBuffers pb{};
 	pb.rec_first = src;

@@ -216,7 +216,7 @@ histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_
 // K2: one CTA, 256 threads; thread d owns bin d of every column.
 template <int ES>
 __global__ void __launch_bounds__(kBins, 1)
-setup_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, KeyDesc kd, WsHead *ws) {
+setup_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, KeyDesc kd, WsHead *ws, Ctl *host_ctl) {
 	__shared__ unsigned long long s_warp[8];
 	__shared__ uint32_t s_live[kMaxCols];
 	const uint32_t d = threadIdx.x, lane = d & 31u, warp = d >> 5;
@@ -260,6 +260,8 @@ setup_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, KeyDesc k
 		ctl.pad = 0;
 		ctl.n = n;
 		ws->ctl = ctl;
+		if (host_ctl != nullptr)
+			*host_ctl = ctl; // mapped pinned memory: the host reads it after the stream has drained
 	}
 }
 
@@ -320,13 +322,13 @@ cudaError_t launch_histogram(const void *src, size_t n, uint32_t record_bytes, c
 }
 
 cudaError_t launch_setup(const void *src, size_t n, uint32_t record_bytes, const KeyDesc &kd,
-                         WsHead *ws, cudaStream_t st) {
+                         WsHead *ws, Ctl *host_ctl, cudaStream_t st) {
 	switch (record_bytes) {
-	case 1: setup_kernel<1><<<1, kBins, 0, st>>>(static_cast<const uint8_t *>(src), n, kd, ws); break;
-	case 2: setup_kernel<2><<<1, kBins, 0, st>>>(static_cast<const uint16_t *>(src), n, kd, ws); break;
-	case 4: setup_kernel<4><<<1, kBins, 0, st>>>(static_cast<const uint32_t *>(src), n, kd, ws); break;
-	case 8: setup_kernel<8><<<1, kBins, 0, st>>>(static_cast<const unsigned long long *>(src), n, kd, ws); break;
-	case 16: setup_kernel<16><<<1, kBins, 0, st>>>(static_cast<const ulonglong2 *>(src), n, kd, ws); break;
+	case 1: setup_kernel<1><<<1, kBins, 0, st>>>(static_cast<const uint8_t *>(src), n, kd, ws, host_ctl); break;
+	case 2: setup_kernel<2><<<1, kBins, 0, st>>>(static_cast<const uint16_t *>(src), n, kd, ws, host_ctl); break;
+	case 4: setup_kernel<4><<<1, kBins, 0, st>>>(static_cast<const uint32_t *>(src), n, kd, ws, host_ctl); break;
+	case 8: setup_kernel<8><<<1, kBins, 0, st>>>(static_cast<const unsigned long long *>(src), n, kd, ws, host_ctl); break;
+	case 16: setup_kernel<16><<<1, kBins, 0, st>>>(static_cast<const ulonglong2 *>(src), n, kd, ws, host_ctl); break;
 	default: return cudaErrorInvalidValue;
 	}
 	count_launch();

@@ -77,8 +77,9 @@ struct PassGeometry {
 cudaError_t launch_histogram(const void *src, size_t n, uint32_t record_bytes, const KeyDesc &kd,
                              WsHead *ws, int num_sms, cudaStream_t st);
 
+// host_ctl: mapped pinned mirror of ws->ctl (may be null)
 cudaError_t launch_setup(const void *src, size_t n, uint32_t record_bytes, const KeyDesc &kd,
-                         WsHead *ws, cudaStream_t st);
+                         WsHead *ws, Ctl *host_ctl, cudaStream_t st);
 
 // status: look-back words for this column, tiles * 256 entries of 4 (n < 2^30) or 8 bytes, zeroed.
 // ctl == nullptr: forced pass (ordinal 0, never skipped) for rsx_scatter_pass.

@@ -54,7 +54,7 @@ template <int ES, int PL, class Cfg> struct Scatter2Smem {
 template <int ES, int PL, int V> struct Cfg2V
 	: Cfg2T<((ES + PL > 4 && ES + PL <= 8) ? 256 : 512),
 	        ((ES + PL <= 4) ? 22 : (ES + PL <= 8) ? 32 : (ES + PL <= 16) ? 8 : 6), 2, 8, ((ES + PL > 4 && ES + PL <= 8) ? 1 : 0)> {};
-constexpr int kNumVariants2 = 20;
+constexpr int kNumVariants2 = 24;
 template <> struct Cfg2V<4, 0, 1> : Cfg2T<512, 20, 2, 8> {};
 template <> struct Cfg2V<4, 0, 2> : Cfg2T<384, 24, 2, 8> {};
 template <> struct Cfg2V<4, 0, 3> : Cfg2T<256, 22, 4, 8> {};
@@ -84,6 +84,15 @@ template <> struct Cfg2V<4, 0, 16> : Cfg2T<384, 20, 3, 8, 1> {};
 template <> struct Cfg2V<4, 0, 17> : Cfg2T<384, 32, 2, 8, 1> {};
 template <> struct Cfg2V<4, 0, 18> : Cfg2T<512, 30, 2, 8, 1> {};
 template <> struct Cfg2V<4, 0, 19> : Cfg2T<640, 22, 1, 8, 1> {};
+// 20..23: small tiles for mid-size inputs (a few hundred thousand to a few million records)
+template <> struct Cfg2V<4, 0, 20> : Cfg2T<256, 11, 4, 8, 0> {};
+template <> struct Cfg2V<4, 0, 21> : Cfg2T<256, 8, 6, 8, 0> {};
+template <> struct Cfg2V<4, 0, 22> : Cfg2T<256, 16, 4, 8, 0> {};
+template <> struct Cfg2V<4, 0, 23> : Cfg2T<512, 11, 2, 8, 0> {};
+template <> struct Cfg2V<8, 0, 20> : Cfg2T<256, 6, 4, 8, 0> {};
+template <> struct Cfg2V<8, 0, 21> : Cfg2T<256, 8, 4, 8, 0> {};
+template <> struct Cfg2V<8, 0, 22> : Cfg2T<256, 12, 3, 8, 0> {};
+template <> struct Cfg2V<8, 0, 23> : Cfg2T<512, 6, 2, 8, 0> {};
 template <> struct Cfg2V<8, 0, 10> : Cfg2T<512, 12, 2, 8, 1> {};
 template <> struct Cfg2V<8, 0, 11> : Cfg2T<512, 16, 2, 8, 1> {};
 template <> struct Cfg2V<8, 0, 12> : Cfg2T<384, 20, 2, 8, 1> {};
@@ -102,6 +111,9 @@ template <int ES, int PL> struct PreferV2 { static constexpr bool value = false;
 // 256 threads x 32 records, two CTAs per SM, count + ticket placement -- 4.01 ms per pass of 1 B u64
 // keys against 4.22 ms for the staging kernel, which has room for only one CTA per SM.
 template <> struct PreferV2<8, 0> { static constexpr bool value = true; };
+// u32 keys + u32 index lane (radix_sort_rank on 32-bit keys): 18.6 vs 19.8 ms per 1 B-key rank sort.
+// Every other footprint measured slower than the staging kernel (tools/footprints.py, profiles/r2_variants.md).
+template <> struct PreferV2<4, 4> { static constexpr bool value = true; };
 
 // Streaming load: every record is read exactly once per pass.
 template <typename R> __device__ __forceinline__ R ld_stream(const R *p) { return __ldcs(p); }

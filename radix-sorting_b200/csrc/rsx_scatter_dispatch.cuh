@@ -35,6 +35,10 @@ cudaError_t launch_scatter2_v(const ScatterParams &sp, int num_sms, cudaStream_t
 		case 17: return launch_scatter2_c<ES, PL, DM, OffT, Cfg2V<ES, PL, 17>>(sp, num_sms, st);
 		case 18: return launch_scatter2_c<ES, PL, DM, OffT, Cfg2V<ES, PL, 18>>(sp, num_sms, st);
 		case 19: return launch_scatter2_c<ES, PL, DM, OffT, Cfg2V<ES, PL, 19>>(sp, num_sms, st);
+		case 20: return launch_scatter2_c<ES, PL, DM, OffT, Cfg2V<ES, PL, 20>>(sp, num_sms, st);
+		case 21: return launch_scatter2_c<ES, PL, DM, OffT, Cfg2V<ES, PL, 21>>(sp, num_sms, st);
+		case 22: return launch_scatter2_c<ES, PL, DM, OffT, Cfg2V<ES, PL, 22>>(sp, num_sms, st);
+		case 23: return launch_scatter2_c<ES, PL, DM, OffT, Cfg2V<ES, PL, 23>>(sp, num_sms, st);
 		default: break;
 		}
 	}
