@@ -42,6 +42,10 @@ REC16_U64 = np.dtype([("key", "<u8"), ("payload", "<u8")])                  # u6
 # (no ref_code: checked against the oracle's independent stable sort, not against ref_shim)
 REC16_F64 = np.dtype([("payload", "<u8"), ("key", "<f8")])                  # double key in the 2nd word
 REC16_F32 = np.dtype([("payload", "<u4"), ("key", "<f4"), ("pad", "V8")])   # float key at offset 4
+# record sizes the tile kernels do not move directly (sorted as keys + indices, then one gather)
+REC12_U32 = np.dtype([("key", "<u4"), ("payload", "<u8")])                  # radix_sort_u32.c:7-10 sortrec, packed: 12 bytes
+REC24_F64 = np.dtype([("payload", "<u4"), ("pad", "V8"), ("key", "<f8"), ("tail", "<u4")])  # double key straddling 8-byte words
+REC7_I16 = np.dtype([("payload", "<u4"), ("pad", "V1"), ("key", "<i2")])    # odd size, unaligned signed key
 
 
 @dataclass(frozen=True)
@@ -75,6 +79,9 @@ TYPES = {t.name: t for t in [
     ElemType("rec16_u64", REC16_U64, 16, 0, 8, KDF_UNSIGNED, 12),
     ElemType("rec16_f64", REC16_F64, 16, 8, 8, KDF_FLOAT, -1),
     ElemType("rec16_f32", REC16_F32, 16, 4, 4, KDF_FLOAT, -1),
+    ElemType("rec12_u32", REC12_U32, 12, 0, 4, KDF_UNSIGNED, -1),
+    ElemType("rec24_f64", REC24_F64, 24, 12, 8, KDF_FLOAT, -1),
+    ElemType("rec7_i16", REC7_I16, 7, 5, 2, KDF_SIGNED, -1),
 ]}
 
 

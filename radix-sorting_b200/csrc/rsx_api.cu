@@ -260,6 +260,26 @@ int check_layout(const rsx_layout *L, KeyDesc *kd) {
 	return RSX_OK;
 }
 
+// rsx_sort / rsx_sort_rank also take records the tile kernels cannot move directly: any
+// record_bytes up to kMaxGenericRecord and a key anywhere inside the record.  *generic is set for
+// those; kd then describes the EXTRACTED key (a key_bytes-sized scalar).
+constexpr uint32_t kMaxGenericRecord = 4096;
+int check_layout_any(const rsx_layout *L, KeyDesc *kd, bool *generic) {
+	*generic = false;
+	if (check_layout(L, kd) == RSX_OK)
+		return RSX_OK;
+	if (!L)
+		return RSX_ERR_INVALID;
+	const uint32_t rb = L->record_bytes, kb = L->key_bytes, ko = L->key_offset;
+	if (rb < 1 || rb > kMaxGenericRecord || !(kb == 1 || kb == 2 || kb == 4 || kb == 8) || (uint64_t)ko + kb > rb)
+		return RSX_ERR_INVALID;
+	if (L->kdf_kind > RSX_KDF_FLOAT || (L->flags & ~RSX_FLAG_INVERT) || (L->kdf_kind == RSX_KDF_FLOAT && kb < 4))
+		return RSX_ERR_INVALID;
+	const rsx_layout key_layout = {kb, 0, kb, L->kdf_kind, L->flags};
+	*generic = true;
+	return check_layout(&key_layout, kd);
+}
+
 // Record whose derived key is all ones: pads the last tile so that padding sorts last.
 ulonglong2 pad_record(const KeyDesc &kd) {
 	const unsigned long long m = kd.key_bytes >= 8 ? ~0ULL : ((1ULL << (8 * kd.key_bytes)) - 1ULL);
@@ -599,9 +619,15 @@ int rsx_get_profile(float *ms_out, int cap) {
 
 size_t rsx_workspace_bytes(size_t n, const rsx_layout *layout, int rank_idx_bytes) {
 	KeyDesc kd;
-	if (check_layout(layout, &kd) != RSX_OK)
+	bool generic = false;
+	if (check_layout_any(layout, &kd, &generic) != RSX_OK)
 		return 0;
 	Plan P;
+	if (generic) { // the keys are ranked, the records gathered: the passes see key_bytes-sized records
+		const rsx_layout key_layout = {layout->key_bytes, 0, layout->key_bytes, layout->kdf_kind, layout->flags};
+		make_plan(P, n < 2 ? 2 : n, &key_layout, kd, rank_idx_bytes ? rank_idx_bytes : (n <= 0xFFFFFFFFull ? 4 : 8));
+		return P.total;
+	}
 	make_plan(P, n < 2 ? 2 : n, layout, kd, rank_idx_bytes);
 	return P.total;
 }
@@ -681,10 +707,53 @@ static int sort_device(void *src, void *aux, size_t n, const rsx_layout *layout,
 	return RSX_OK;
 }
 
+static int rank_device(const void *src, void *ib, size_t n, const rsx_layout *layout, const KeyDesc &kd,
+                       int idx_bytes, void **result, rsx_report *rep, cudaStream_t st, int dev, bool staged);
+
+// Records of any size (see check_layout_any): keys are extracted, rank-sorted, and one gather puts
+// every record in its final place -- in the buffer the reference's parity rule designates.
+static int sort_device_generic(void *src, void *aux, size_t n, const rsx_layout *layout, const KeyDesc &kdk,
+                               void **result, rsx_report *rep, cudaStream_t st, int dev, bool staged) {
+	const uint32_t rb = layout->record_bytes, kb = layout->key_bytes;
+	const int idxb = n <= 0xFFFFFFFFull ? 4 : 8;
+	const rsx_layout key_layout = {kb, 0, kb, layout->kdf_kind, layout->flags};
+	const size_t kbytes = align_up(n * kb, 256);
+	StageLease SL;
+	int r = acquire_stage(SL, dev, kbytes + 2 * n * (size_t)idxb);
+	if (r)
+		return r;
+	SL.inflight = st;
+	SL.has_inflight = true;
+	unsigned char *keys = static_cast<unsigned char *>(SL.ptr), *ib = keys + kbytes;
+	const int sms = g_dev[dev].num_sms;
+	CU(launch_extract_keys(src, n, rb, layout->key_offset, kb, keys, sms, st));
+	void *ranks = nullptr;
+	rsx_report local;
+	if (!rep)
+		rep = &local;
+	if ((r = rank_device(keys, ib, n, &key_layout, kdk, idxb, &ranks, rep, st, dev, staged)))
+		return r;
+	rep->kernel_launches += 1;
+	if (rep->early_exit) { // radix_sort.hpp:60-62: nothing moves
+		SL.has_inflight = false;
+		*result = src;
+		return RSX_OK;
+	}
+	CU(launch_gather_records(src, ranks, idxb, aux, n, rb, sms, st));
+	rep->kernel_launches += 1;
+	if (!rep->result_in_aux) // even number of live columns: the reference's result is in src
+		CU(cudaMemcpyAsync(src, aux, n * (size_t)rb, cudaMemcpyDeviceToDevice, st));
+	CU(cudaStreamSynchronize(st));
+	SL.has_inflight = false;
+	*result = rep->result_in_aux ? aux : src;
+	return RSX_OK;
+}
+
 int rsx_sort(void *src, void *aux, size_t n, const rsx_layout *layout, void **result, rsx_report *rep,
              void *stream) {
 	KeyDesc kd;
-	int r = check_layout(layout, &kd);
+	bool generic = false;
+	int r = check_layout_any(layout, &kd, &generic);
 	if (r)
 		return r;
 	if (!result || (n && (!src || !aux)))
@@ -709,8 +778,12 @@ int rsx_sort(void *src, void *aux, size_t n, const rsx_layout *layout, void **re
 	if (ks != ka)
 		return RSX_ERR_MIXED_MEMORY;
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	auto sort_dev = [&](void *s_, void *a_, void **res_, bool staged_) {
+		return generic ? sort_device_generic(s_, a_, n, layout, kd, res_, rep, st, dev, staged_)
+		               : sort_device(s_, a_, n, layout, kd, res_, rep, st, dev, staged_);
+	};
 	if (ks == PK_DEVICE)
-		return sort_device(src, aux, n, layout, kd, result, rep, st, dev, false);
+		return sort_dev(src, aux, result, false);
 
 	// Host buffers: stage through device memory.  The reference sorts host memory in place;
 	// the bytes land in the buffer it would have returned, the other buffer is left as is
@@ -732,7 +805,7 @@ int rsx_sort(void *src, void *aux, size_t n, const rsx_layout *layout, void **re
 	if (e != cudaSuccess)
 		r = fail_cuda(e, "H2D");
 	if (!r)
-		r = sort_device(dsrc, daux, n, layout, kd, &dres, rep, st, dev, true);
+		r = sort_dev(dsrc, daux, &dres, true);
 	if (!r && !rep->early_exit) {
 		void *hres = rep->result_in_aux ? aux : src;
 		e = cudaMemcpyAsync(hres, dres, bytes, cudaMemcpyDeviceToHost, st);
@@ -814,7 +887,8 @@ static int rank_device(const void *src, void *ib, size_t n, const rsx_layout *la
 int rsx_sort_rank(const void *src, void *index_buffer, size_t n, const rsx_layout *layout, int idx_bytes,
                   void **result, rsx_report *rep, void *stream) {
 	KeyDesc kd;
-	int r = check_layout(layout, &kd);
+	bool generic = false;
+	int r = check_layout_any(layout, &kd, &generic);
 	if (r)
 		return r;
 	if (!(idx_bytes == 1 || idx_bytes == 2 || idx_bytes == 4 || idx_bytes == 8))
@@ -846,8 +920,23 @@ int rsx_sort_rank(const void *src, void *index_buffer, size_t n, const rsx_layou
 	if (ks != ki)
 		return RSX_ERR_MIXED_MEMORY;
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	// records of any size: rank the extracted keys (src itself is never written either way)
+	const rsx_layout key_layout = {layout->key_bytes, 0, layout->key_bytes, layout->kdf_kind, layout->flags};
+	auto rank_dev = [&](const void *s_, void *ib_, void **res_, bool staged_) -> int {
+		if (!generic)
+			return rank_device(s_, ib_, n, layout, kd, idx_bytes, res_, rep, st, dev, staged_);
+		void *keys = nullptr;
+		cudaError_t e = cudaMallocAsync(&keys, n * (size_t)layout->key_bytes, st);
+		if (e != cudaSuccess)
+			return fail_cuda(e, "cudaMallocAsync(keys)");
+		e = launch_extract_keys(s_, n, layout->record_bytes, layout->key_offset, layout->key_bytes, keys, g_dev[dev].num_sms, st);
+		int rr = e == cudaSuccess ? rank_device(keys, ib_, n, &key_layout, kd, idx_bytes, res_, rep, st, dev, staged_)
+		                          : fail_cuda(e, "extract_keys");
+		cudaFreeAsync(keys, st);
+		return rr;
+	};
 	if (ks == PK_DEVICE)
-		return rank_device(src, index_buffer, n, layout, kd, idx_bytes, result, rep, st, dev, false);
+		return rank_dev(src, index_buffer, result, false);
 
 	const size_t sbytes = n * layout->record_bytes, ibytes = n * (size_t)idx_bytes;
 	StageLease SL;
@@ -865,7 +954,7 @@ int rsx_sort_rank(const void *src, void *index_buffer, size_t n, const rsx_layou
 	if (e != cudaSuccess)
 		r = fail_cuda(e, "H2D");
 	if (!r)
-		r = rank_device(dsrc, dib, n, layout, kd, idx_bytes, &dres, rep, st, dev, true);
+		r = rank_dev(dsrc, dib, &dres, true);
 	unsigned char *hres = static_cast<unsigned char *>(index_buffer);
 	if (!r) {
 		hres += rep->result_in_aux ? ibytes : 0;

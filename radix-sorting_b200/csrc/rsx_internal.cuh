@@ -103,6 +103,12 @@ cudaError_t launch_iota_if_early(void *index_buffer, int idx_bytes, size_t n, co
 cudaError_t launch_narrow_index(const uint32_t *wide0, const uint32_t *wide1, void *index_buffer,
                                 int idx_bytes, size_t n, const Ctl *ctl, cudaStream_t st);
 
+// records of any size: key extraction + final gather around a rank sort of the keys
+cudaError_t launch_extract_keys(const void *recs, size_t n, uint32_t record_bytes, uint32_t key_offset, uint32_t key_bytes,
+                                void *keys_out, int num_sms, cudaStream_t st);
+cudaError_t launch_gather_records(const void *src, const void *rank, int idx_bytes, void *dst, size_t n, uint32_t record_bytes,
+                                  int num_sms, cudaStream_t st);
+
 // key-range routing counts (d_counts: 16 zeroed entries)
 cudaError_t launch_split_counts(const void *data, size_t n, uint32_t record_bytes, const KeyDesc &kd,
                                 const unsigned long long *d_split, uint32_t nsplit, unsigned long long *d_counts,

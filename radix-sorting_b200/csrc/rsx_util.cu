@@ -202,6 +202,34 @@ __global__ void __launch_bounds__(512) ticket_probe_kernel(unsigned long long *m
 		atomicAdd(mismatch, bad);
 }
 
+// ---- records of any size (12-byte {u32 key, 64-bit payload} on ILP32, 24-byte rows, ...) --------
+// The tile kernels move records of 1/2/4/8/16 bytes.  Every other size -- and keys that straddle
+// an 8-byte word -- is sorted as: extract the keys, rank-sort them (keys + indices travel through
+// the passes, the records stay put), then ONE gather moves each record to its final place.
+template <typename K>
+__global__ void extract_keys_kernel(const unsigned char *__restrict__ recs, size_t n, uint32_t rb, uint32_t ko, K *__restrict__ out) {
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const unsigned char *p = recs + i * rb + ko;
+		K k = 0;
+#pragma unroll
+		for (int b = 0; b < (int)sizeof(K); ++b)
+			k |= (K)p[b] << (8 * b);
+		out[i] = k;
+	}
+}
+
+// dst[i] = src[rank[i]], W-byte words (W = 4 when record size and both buffers allow it, else 1)
+template <typename I, typename W>
+__global__ void gather_records_kernel(const W *__restrict__ src, const I *__restrict__ rank, W *__restrict__ dst, size_t n,
+                                      uint32_t words_per_rec) {
+	const size_t total = n * words_per_rec;
+	for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+		const size_t i = w / words_per_rec;
+		const uint32_t j = (uint32_t)(w - i * words_per_rec);
+		dst[w] = src[(size_t)rank[i] * words_per_rec + j];
+	}
+}
+
 inline int grid_for(size_t n, int threads, int cap) {
 	size_t g = (n + threads - 1) / threads;
 	if (g < 1) g = 1;
@@ -291,4 +319,41 @@ cudaError_t launch_verify(const void *data, size_t n, uint32_t record_bytes, con
 	return cudaGetLastError();
 }
 
+} // namespace rsx
+
+namespace rsx {
+cudaError_t launch_extract_keys(const void *recs, size_t n, uint32_t record_bytes, uint32_t key_offset, uint32_t key_bytes,
+                                void *keys_out, int num_sms, cudaStream_t st) {
+	const int g = grid_for(n, 256, num_sms * 16);
+	const unsigned char *r = static_cast<const unsigned char *>(recs);
+	switch (key_bytes) {
+	case 1: extract_keys_kernel<<<g, 256, 0, st>>>(r, n, record_bytes, key_offset, static_cast<uint8_t *>(keys_out)); break;
+	case 2: extract_keys_kernel<<<g, 256, 0, st>>>(r, n, record_bytes, key_offset, static_cast<uint16_t *>(keys_out)); break;
+	case 4: extract_keys_kernel<<<g, 256, 0, st>>>(r, n, record_bytes, key_offset, static_cast<uint32_t *>(keys_out)); break;
+	case 8: extract_keys_kernel<<<g, 256, 0, st>>>(r, n, record_bytes, key_offset, static_cast<unsigned long long *>(keys_out)); break;
+	default: return cudaErrorInvalidValue;
+	}
+	count_launch();
+	return cudaGetLastError();
+}
+
+cudaError_t launch_gather_records(const void *src, const void *rank, int idx_bytes, void *dst, size_t n, uint32_t record_bytes,
+                                  int num_sms, cudaStream_t st) {
+	const bool words = record_bytes % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
+	const uint32_t wpr = words ? record_bytes / 4 : record_bytes;
+	const int g = grid_for(n * wpr, 256, num_sms * 16);
+	if (words) {
+		if (idx_bytes == 4)
+			gather_records_kernel<<<g, 256, 0, st>>>(static_cast<const uint32_t *>(src), static_cast<const uint32_t *>(rank), static_cast<uint32_t *>(dst), n, wpr);
+		else
+			gather_records_kernel<<<g, 256, 0, st>>>(static_cast<const uint32_t *>(src), static_cast<const unsigned long long *>(rank), static_cast<uint32_t *>(dst), n, wpr);
+	} else {
+		if (idx_bytes == 4)
+			gather_records_kernel<<<g, 256, 0, st>>>(static_cast<const uint8_t *>(src), static_cast<const uint32_t *>(rank), static_cast<uint8_t *>(dst), n, wpr);
+		else
+			gather_records_kernel<<<g, 256, 0, st>>>(static_cast<const uint8_t *>(src), static_cast<const unsigned long long *>(rank), static_cast<uint8_t *>(dst), n, wpr);
+	}
+	count_launch();
+	return cudaGetLastError();
+}
 } // namespace rsx

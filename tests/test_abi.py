@@ -97,7 +97,7 @@ def test_workspace_sizing_and_options_need_no_device(rsx):
     wr = L.rsx_workspace_bytes(n, C.byref(u32), 4)
     assert wr >= w32 + 2 * n * 4 and wr - 2 * n * 4 < 2 * w32  # (key + index tiles are smaller: more look-back rows)
     assert L.rsx_workspace_bytes(n, C.byref(u32), 2) >= wr + 2 * n * 4  # narrow index types sort through u32 lanes
-    bad = rsx.RsxLayout(3, 0, 1, 0, 0)
+    bad = rsx.RsxLayout(12, 0, 3, 0, 0)  # 12-byte records are fine (keys + gather path), a 3-byte key is not
     assert L.rsx_workspace_bytes(n, C.byref(bad), 0) == 0
     # options are validated on the host
     assert L.rsx_set_option(b"scatter_variant", 99) == rsx.RSX_ERR_INVALID

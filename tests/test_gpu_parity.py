@@ -482,6 +482,33 @@ def test_float_key_inside_16_byte_record(rsx, torch, oracle, tname, n):
     assert np.array_equal(ranks, wr) and rrep.result_in_aux == worep.result_in_aux
 
 
+@pytest.mark.parametrize("tname", ["rec12_u32", "rec24_f64", "rec7_i16"])
+@pytest.mark.parametrize("n,dist,mask", [(2, "uniform", -1), (1000, "uniform", -1), (300007, "uniform", 0xFFFFF), (300007, "and3", -1),
+                                          (50000, "sorted", -1), (2_000_003, "uniform", -1)])
+def test_records_of_any_size(rsx, torch, oracle, tname, n, dist, mask):
+    """Record sizes the tile kernels do not move (12-byte {u32 key, 64-bit payload} like
+    radix_sort_u32.c:7-10 on ILP32, a double key straddling two 8-byte words, a 7-byte record):
+    keys are ranked, records gathered once; result and returned buffer as the reference's
+    radix_sort<T> would give (device and host buffers, value and rank sort)."""
+    t = TYPES[tname]
+    data = make_input(tname, n, 17, dist, mask & ((1 << 64) - 1))
+    for desc in (False, True):
+        out, rep, in_aux = gpu_sort(rsx, torch, tname, data, descending=desc)
+        want, orep, _ = oracle.radix_sort(data, t.layout(descending=desc))
+        assert out.tobytes() == want.tobytes(), (tname, n, desc)
+        assert rep.result_in_aux == orep.result_in_aux == int(in_aux) and rep.early_exit == orep.early_exit
+    ranks, rrep, _ = gpu_rank(rsx, torch, tname, data, np.uint32)
+    wr, worep, _ = oracle.radix_sort_rank(data, t.layout(), np.uint32)
+    assert np.array_equal(ranks, wr) and rrep.result_in_aux == worep.result_in_aux
+    if n <= 300007:  # host buffers: staged
+        raw = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+        src = torch.from_numpy(raw.copy())
+        aux = torch.zeros_like(src)
+        res = rsx.radix_sort(src, aux, None, kf_for(rsx, tname))
+        want, _, _ = oracle.radix_sort(data, t.layout())
+        assert res.numpy().tobytes() == want.tobytes()
+
+
 def test_multipass_composite_key_like_listing5(rsx, torch, oracle):
     """radix_sort_u64_multipass.c:117-118 sorts a 64-bit key with two stable 32-bit sorts (low half,
     then high half).  The same composition through key_offset/key_bytes windows must equal one

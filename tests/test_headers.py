@@ -1,5 +1,6 @@
 """The C++ drop-in headers (include/radix_sort.hpp, radix_sort_rank.hpp, radix_sort_basic_kdf.hpp):
 host-side mirror of the reference interface over the C ABI."""
+import importlib
 import os
 import subprocess
 import textwrap
@@ -96,11 +97,51 @@ def test_reference_scenarios_on_gpu(built):
     assert r.returncode == 0 and "All tests OK." in r.stdout, r.stdout + r.stderr
 
 
+def _fnv1a(buf):
+    """64-bit FNV-1a of a uint8 array, through a 10-line C helper compiled once (a Python loop over
+    up to 160 MB would take minutes)."""
+    import ctypes as C
+    import tempfile
+    global _FNV
+    if "_FNV" not in globals():
+        d = tempfile.mkdtemp()
+        src = os.path.join(d, "fnv.c")
+        open(src, "w").write("#include <stdint.h>\n#include <stddef.h>\nuint64_t fnv(const unsigned char*b,size_t n){uint64_t h="
+                             "0xCBF29CE484222325ULL;for(size_t i=0;i<n;++i)h=(h^b[i])*0x100000001B3ULL;return h;}\n")
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", os.path.join(d, "fnv.so"), src])
+        _FNV = C.CDLL(os.path.join(d, "fnv.so"))
+        _FNV.fnv.restype = C.c_uint64
+        _FNV.fnv.argtypes = [C.c_void_p, C.c_size_t]
+    return int(_FNV.fnv(buf.ctypes.data, buf.shape[0]))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("args", [["1000000"], ["0", "0", "0", "uint32_t", "00FFFFFF"], ["3000000", "0", "0", "uint64_t"],
                                   ["2000000", "0", "0", "float"], ["2000000", "0", "0", "int64_t"], ["65536", "0", "0", "uint8_t"],
                                   ["70000", "0", "0", "uint16_t"], ["1000000", "0", "0", "double"], ["1000000", "0", "0", "int32_t"]])
 def test_radix_cli_on_gpu(built, tmp_path, args):
+    """N1: the `radix` CLI on the device path.  Its output digest must equal the ORACLE's radix_sort
+    of the same seeded key bytes (radix_experiment.cpp:203-223 only checks "is it ordered")."""
+    import re
+    import numpy as np
+    import pyoracle
+    keygen = importlib.import_module("radix-sorting_b200.keygen")
     r = subprocess.run([os.path.join(built, "radix_b200"), *args], capture_output=True, text=True, timeout=300,
                        cwd=str(tmp_path))
-    assert r.returncode == 0 and "device-resident" in r.stdout, r.stdout + r.stderr
+    assert r.returncode == 0 and "device-resident" in r.stdout and "CPU yardstick" in r.stdout, r.stdout + r.stderr
+    m = re.search(r"digest fnv1a64=([0-9a-f]{16})", r.stdout)
+    assert m, r.stdout
+    tname = {"uint8_t": "u8", "uint16_t": "u16", "uint32_t": "u32", "uint64_t": "u64", "int32_t": "i32", "int64_t": "i64",
+             "float": "f32", "double": "f64"}[args[3] if len(args) > 3 else "uint32_t"]
+    t = pyoracle.TYPES[tname]
+    raw = keygen.fill(1, 0, 160_000_000 // 8, 8).view(np.uint8)  # the CLI's seeded stand-in for 40M_32bit_keys.dat
+    n = raw.shape[0] // t.record_bytes
+    if int(args[0]):
+        n = min(n, int(args[0]))
+    data = raw[: n * t.record_bytes].view(t.dtype).copy()
+    if len(args) > 4:
+        u = data.view(f"<u{t.record_bytes}")
+        u &= np.array(int(args[4], 16) & ((1 << (8 * t.record_bytes)) - 1), dtype=u.dtype)
+    want, _, _ = pyoracle.Oracle().radix_sort(data, t.layout())
+    code = _fnv1a(np.ascontiguousarray(want).view(np.uint8))
+    assert f"{code:016x}" == m.group(1), "CLI output differs from the oracle's radix_sort"

@@ -1,7 +1,9 @@
 /*
 	radix_b200.cpp -- GPU counterpart of the reference's `radix` experiment harness
 	(radix_experiment.cpp:176-285): same positional arguments, same key-file format, now timing
-	the device path next to nothing else (the CPU reference is timed by bench.py).
+	the device path with a CPU yardstick beside it: std::stable_sort by the same derived key on one
+	host core, whose output is byte-identical to the reference's radix_sort (SURVEY.md finding 1) and
+	therefore doubles as the verification (memcmp, not just "is it ordered", radix_experiment.cpp:208-212).
 
 	    ./radix_b200 <count> [<use_mmap> <use_huge> <type> <hex-mask>]
 
@@ -10,7 +12,8 @@
 	(raw little-endian bytes, reference Makefile:79-82) in the current directory; if it is
 	missing, 160 000 000 seeded bytes are generated instead (the reference file is /dev/urandom
 	output and cannot be reproduced).  Prints one time for the host-buffer call (H2D + sort +
-	D2H, what a drop-in user sees) and one for device-resident buffers.
+	D2H, what a drop-in user sees), one for device-resident buffers, the CPU yardstick's time and a
+	64-bit FNV-1a digest of the sorted bytes (tests/test_headers.py compares it with the oracle's).
 */
 #include <algorithm>
 #include <chrono>
@@ -49,6 +52,14 @@ static std::vector<unsigned char> load_keys(const char *fn) {
 		printf("'%s' not found: generated %zu seeded bytes.\n", fn, buf.size());
 	}
 	return buf;
+}
+
+static uint64_t fnv1a(const void *p, size_t bytes) {
+	const unsigned char *b = static_cast<const unsigned char *>(p);
+	uint64_t h = 0xCBF29CE484222325ULL;
+	for (size_t i = 0; i < bytes; ++i)
+		h = (h ^ b[i]) * 0x100000001B3ULL;
+	return h;
 }
 
 template <typename T> static bool verify(const T *keys, size_t n) {
@@ -94,6 +105,17 @@ template <typename T> static int run(const std::vector<unsigned char> &file, siz
 		return 1;
 	const double host_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
 
+	// CPU yardstick + verification: a stable sort by the derived key (one core)
+	std::vector<T> cpu(pristine);
+	auto c0 = std::chrono::steady_clock::now();
+	std::stable_sort(cpu.begin(), cpu.end(), [](const T &a, const T &b) { return basic_kdfs::kdf(a) < basic_kdfs::kdf(b); });
+	auto c1 = std::chrono::steady_clock::now();
+	const double cpu_ms = std::chrono::duration<double, std::milli>(c1 - c0).count();
+	if (memcmp(cpu.data(), sorted, n * sizeof(T)) != 0) {
+		printf("Sort differs from std::stable_sort by derived key (host buffers).\n");
+		return 1;
+	}
+
 	T *dsrc, *daux;
 	cudaMalloc((void **)&dsrc, n * sizeof(T));
 	cudaMalloc((void **)&daux, n * sizeof(T));
@@ -113,6 +135,14 @@ template <typename T> static int run(const std::vector<unsigned char> &file, siz
 			best = ms;
 		if (!dres)
 			return 2;
+		if (r == 3) { // the device-resident result, byte for byte
+			std::vector<T> back(n);
+			cudaMemcpy(back.data(), dres, n * sizeof(T), cudaMemcpyDeviceToHost);
+			if (memcmp(cpu.data(), back.data(), n * sizeof(T)) != 0) {
+				printf("Sort differs from std::stable_sort by derived key (device buffers).\n");
+				return 1;
+			}
+		}
 	}
 	const size_t np = std::min<size_t>(n, 10);
 	for (size_t i = 0; i < np; ++i) {
@@ -122,6 +152,9 @@ template <typename T> static int run(const std::vector<unsigned char> &file, siz
 	}
 	printf("Sorted %zu entries in %.4f ms (host buffers: H2D + sort + D2H), %.1f Mkeys/s\n", n, host_ms, n / host_ms / 1e3);
 	printf("Sorted %zu entries in %.4f ms (device-resident buffers), %.1f Mkeys/s\n", n, best, n / best / 1e3);
+	printf("Sorted %zu entries in %.4f ms (CPU yardstick: std::stable_sort by derived key, 1 core), %.1f Mkeys/s; "
+	       "device outputs memcmp-equal\n", n, cpu_ms, n / cpu_ms / 1e3);
+	printf("digest fnv1a64=%016" PRIx64 "\n", fnv1a(sorted, n * sizeof(T)));
 	cudaFreeHost(src);
 	cudaFreeHost(aux);
 	cudaFree(dsrc);
