@@ -36,6 +36,8 @@ WORKLOADS = {
     "256M-u32-uniform": ("u32", 256_000_000, "uniform", _M64, 0, 4),       # profiling size (ncu replays)
     "256M-u64-uniform": ("u64", 256_000_000, "uniform", _M64, 0, 8),
     "1B-u32-mask24": ("u32", 1_000_000_000, "uniform", 0x00FFFFFF, 0, 3),  # column skipping, README.md:889-891
+    "1B-u32-nibbles": ("u32", 1_000_000_000, "uniform", 0x0F0F0F0F, 0, 4),  # N4: 16 varying bits in 4 live byte columns
+    "1B-u64-nibbles": ("u64", 1_000_000_000, "uniform", 0x0F0F0F0F0F0F0F0F, 0, 8),
     "1B-u64-consthi": ("u64", 1_000_000_000, "uniform", 0x000000FFFFFFFFFF, 0xAA00000000000000, 5),
     "500M-f32": ("f32", 500_000_000, "uniform", _M64, 0, 4),               # BASELINE configs[2]
     "500M-i64": ("i64", 500_000_000, "uniform", _M64, 0, 8),

@@ -63,6 +63,8 @@ typedef struct rsx_report {
 	uint32_t result_in_aux;/* 1 <=> result pointer is aux / index_buffer + n (radix_sort.hpp:89-92) */
 	uint32_t kernel_launches; /* kernels launched by this call                             */
 	uint32_t staged;       /* 1 <=> host buffers were staged through device memory         */
+	uint32_t compacted_passes; /* != 0: key compaction ran -- the varying key bits were gathered and
+	                              sorted in this many passes instead of ncols (README.md:716-758) */
 } rsx_report;
 
 /* ---- value sort --------------------------------------------------------------------------
@@ -262,7 +264,8 @@ uint64_t rsx_total_kernel_launches(void); /* process-wide count, for bench.py's 
  * ticket ranking or the ballot ranking, 0 force ticket, 1 force ballot; DESIGN.md "K3");
  * "query_rank_mode" returns the mode in effect (0 / 1).  "scatter_variant" (0..5) selects a tile
  * geometry used in tuning sweeps, "force_wide" (0/1) runs the n >= 2^30 (64-bit offset) kernels
- * at any n (tests).  "profile" (0/1): bracket every kernel of rsx_sort / rsx_sort_rank with CUDA events on
+ * at any n (tests).  "compact_min_n": key compaction is considered for keys-only sorts of at least
+ * this many 4/8-byte keys (default 2^24; <= 0 disables it).  "profile" (0/1): bracket every kernel of rsx_sort / rsx_sort_rank with CUDA events on
  * the launch stream so that per-kernel device times can be read back with rsx_get_profile
  * (bench.py's roofline leg; off by default because the extra events perturb nothing but are
  * not free). */

@@ -55,7 +55,7 @@ class RsxReport(C.Structure):
     """struct rsx_report (include/rsx.h)."""
     _fields_ = [("early_exit", C.c_uint32), ("ncols", C.c_uint32), ("live_mask", C.c_uint32),
                 ("result_in_aux", C.c_uint32), ("kernel_launches", C.c_uint32),
-                ("staged", C.c_uint32)]
+                ("staged", C.c_uint32), ("compacted_passes", C.c_uint32)]
 
 
 RSX_MAX_RANKS = 16

@@ -22,6 +22,7 @@ namespace rsx {
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<int> g_force_wide{0};
 static std::atomic<int> g_small_path{1};
+static std::atomic<long> g_compact_min_n{1L << 24}; // rsx_set_option("compact_min_n", n); <= 0 disables
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 namespace {
@@ -412,6 +413,7 @@ int read_ctl(Lease &L, cudaStream_t st, unsigned long long launches0, rsx_report
 		rep->result_in_aux = pinned->early_exit ? 0 : (pinned->ncols & 1u);
 		rep->kernel_launches = (uint32_t)(g_launches.load() - launches0);
 		rep->staged = staged;
+		rep->compacted_passes = 0;
 	}
 	return RSX_OK;
 }
@@ -599,6 +601,10 @@ int rsx_set_option(const char *name, long value) {
 		g_small_path.store(value ? 1 : 0);
 		return RSX_OK;
 	}
+	if (name && strcmp(name, "compact_min_n") == 0) { // key compaction for keys-only sorts of >= value keys; <= 0: never
+		g_compact_min_n.store(value > 0 ? value : (1L << 62));
+		return RSX_OK;
+	}
 	if (name && strcmp(name, "force_wide") == 0) { // tests: run the n >= 2^30 (64-bit offset) kernels at small n
 		g_force_wide.store(value ? 1 : 0);
 		return RSX_OK;
@@ -659,6 +665,98 @@ void rsx_release(void) {
 	}
 }
 
+// ---- key compaction (N4) ---------------------------------------------------------------------------
+
+// Runs of contiguous varying bits -> Compaction.  More than kMaxRuns runs are merged across the
+// smallest gaps (a constant bit inside a run is harmless: it is the same in every key).  Returns
+// false when compaction would not save at least two passes.
+static bool plan_compaction(const Ctl &c, const KeyDesc &kd, Compaction *out) {
+	const unsigned long long m = kd.key_bytes >= 8 ? ~0ULL : ((1ULL << (8 * kd.key_bytes)) - 1ULL);
+	const unsigned long long varying = c.key_or & c.key_nand & m;
+	if (varying == 0 || c.ncols < 3)
+		return false;
+	struct Run { uint32_t lo, hi; }; // bits [lo, hi)
+	Run runs[64];
+	int nr = 0;
+	for (uint32_t b = 0; b < 8 * kd.key_bytes;) {
+		if (!((varying >> b) & 1ULL)) {
+			++b;
+			continue;
+		}
+		uint32_t e = b;
+		while (e < 8 * kd.key_bytes && ((varying >> e) & 1ULL))
+			++e;
+		runs[nr++] = {b, e};
+		b = e;
+	}
+	while (nr > kMaxRuns) { // merge the two neighbours with the smallest gap
+		int best = 0;
+		for (int i = 1; i + 1 < nr; ++i)
+			if (runs[i + 1].lo - runs[i].hi < runs[best + 1].lo - runs[best].hi)
+				best = i;
+		runs[best].hi = runs[best + 1].hi;
+		for (int i = best + 1; i + 1 < nr; ++i)
+			runs[i] = runs[i + 1];
+		--nr;
+	}
+	Compaction k{};
+	unsigned long long covered = 0;
+	uint32_t at = 0;
+	for (int i = 0; i < nr; ++i) {
+		k.src_shift[i] = runs[i].lo;
+		k.width[i] = runs[i].hi - runs[i].lo;
+		k.dst_shift[i] = at;
+		at += k.width[i];
+		covered |= (k.width[i] >= 64 ? ~0ULL : ((1ULL << k.width[i]) - 1ULL)) << runs[i].lo;
+	}
+	k.nruns = (uint32_t)nr;
+	k.bits = at;
+	k.const_bits = c.key_or & ~covered & m; // constant bits: set in every key or in none
+	const uint32_t passes = (at + 7) / 8;
+	if (passes + 2 > c.ncols)
+		return false;
+	*out = k;
+	return true;
+}
+
+// src holds the original keys (K1/K2 have run).  K1c writes the compacted keys to aux and their
+// digit histograms to the workspace, the ordinary passes sort them (only ceil(bits/8) columns are
+// live), and the expansion puts the original keys into the buffer the reference returns.
+static int sort_compacted(void *src, void *aux, const Plan &P, unsigned char *wsp, Lease &L, const Compaction &cmp,
+                          const Ctl &first, int sms, cudaStream_t st) {
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
+	KeyDesc plain = P.kd; // compacted keys are plain unsigned values
+	plain.kdf_kind = RSX_KDF_UNSIGNED;
+	plain.invert = 0;
+	Plan Pc = P;
+	Pc.kd = plain;
+	CU(zero_workspace(P, wsp, st));
+	prof_mark(st, true);
+	CU(launch_histogram(src, P.n, P.rb, P.kd, ws, sms, st, &cmp, aux));
+	prof_mark(st);
+	CU(launch_setup(aux, P.n, P.rb, plain, ws, L.pinned, st));
+	prof_mark(st);
+	PassBuffers pb{};
+	pb.rec_first = aux;
+	pb.rec_buf[0] = src;
+	pb.rec_buf[1] = aux;
+	int r = enqueue_passes(pb, Pc, wsp, sms, st);
+	if (r)
+		return r;
+	const uint32_t passes = (cmp.bits + 7) / 8; // every compacted column is live by construction
+	void *sorted = (passes & 1u) ? src : aux;
+	void *target = (first.ncols & 1u) ? aux : src; // radix_sort.hpp:89-92 with the reference's column count
+	CU(launch_expand_keys(sorted, target, P.n, P.kd, cmp, sms, st));
+	CU(cudaStreamSynchronize(st));
+	L.drained();
+	prof_collect();
+	if (L.pinned->ncols != passes || L.pinned->early_exit) {
+		snprintf(t_err, sizeof(t_err), "key compaction: expected %u live columns, the device found %u", passes, L.pinned->ncols);
+		return RSX_ERR_CUDA;
+	}
+	return RSX_OK;
+}
+
 // ---- value sort --------------------------------------------------------------------------------
 static int sort_device(void *src, void *aux, size_t n, const rsx_layout *layout, const KeyDesc &kd,
                        void **result, rsx_report *rep, cudaStream_t st, int dev, bool staged) {
@@ -692,15 +790,36 @@ static int sort_device(void *src, void *aux, size_t n, const rsx_layout *layout,
 	const int sms = g_dev[dev].num_sms;
 	if ((r = enqueue_front(src, P, wsp, L.pinned, sms, st)))
 		return r;
+	rsx_report local;
+	if (!rep)
+		rep = &local;
+	// Key compaction (README.md:716-758) for large keys-only sorts: one early look at what K1 found.
+	// If the bits that vary over the input fit in at least two fewer 8-bit columns than the live
+	// byte columns, the keys are compacted and sorted in that many fewer passes.
+	if (layout->record_bytes == kd.key_bytes && kd.key_bytes >= 4 && n >= (size_t)g_compact_min_n.load(std::memory_order_relaxed)) {
+		CU(cudaStreamSynchronize(st));
+		const Ctl first = *L.pinned;
+		Compaction cmp;
+		if (!first.early_exit && plan_compaction(first, kd, &cmp)) {
+			rep->early_exit = 0;
+			rep->ncols = first.ncols;
+			rep->live_mask = first.live_mask;
+			rep->result_in_aux = first.ncols & 1u; // the reference's rule, on ITS column count
+			rep->staged = staged;
+			if ((r = sort_compacted(src, aux, P, wsp, L, cmp, first, sms, st)))
+				return r;
+			rep->kernel_launches = (uint32_t)(g_launches.load() - l0);
+			rep->compacted_passes = (cmp.bits + 7) / 8;
+			*result = rep->result_in_aux ? aux : src;
+			return RSX_OK;
+		}
+	}
 	PassBuffers pb{};
 	pb.rec_first = src;
 	pb.rec_buf[0] = aux; // pass 0: src -> aux, pass 1: aux -> src, ... (radix_sort.hpp:89)
 	pb.rec_buf[1] = src;
 	if ((r = enqueue_passes(pb, P, wsp, sms, st)))
 		return r;
-	rsx_report local;
-	if (!rep)
-		rep = &local;
 	if ((r = read_ctl(L, st, l0, rep, staged)))
 		return r;
 	*result = rep->result_in_aux ? aux : src;

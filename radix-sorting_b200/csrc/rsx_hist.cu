@@ -18,6 +18,7 @@
 //     packed two per word (128 KiB), flushed before a copy can reach 65535.
 //   * descents (kdf(a[i]) > kdf(a[i+1])) are counted on the fly: inside a thread's vector,
 //     across lanes with a shuffle, across warps with one extra scalar load by lane 31.
+#include <algorithm>
 #include <type_traits>
 
 #include "rsx_device.cuh"
@@ -69,6 +70,13 @@ __device__ __forceinline__ KT derive_fast(const typename Rec<ES>::type &r, const
 	return k;
 }
 
+template <typename KT> __device__ __forceinline__ KT compact_key(KT k, const Compaction &c) {
+	KT out = 0;
+	for (uint32_t i = 0; i < c.nruns; ++i)
+		out |= ((k >> c.src_shift[i]) & (KT)((1ULL << c.width[i]) - 1ULL)) << c.dst_shift[i];
+	return out;
+}
+
 // One increment per column.  `lane_base` already contains the lane's bank offset, so each
 // digit costs a shift, a mask, an add and the shared atomic.
 template <int KB, typename KT>
@@ -113,11 +121,12 @@ __device__ __forceinline__ void hist_flush(uint32_t *sh, unsigned long long *ghi
 	}
 }
 
-template <int ES, int KB>
+template <int ES, int KB, bool COMPACT>
 __global__ void __launch_bounds__(kHistThreads, 1)
 histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_t head, size_t n_vec,
                  KeyXform<std::conditional_t<(KB > 4), unsigned long long, uint32_t>> xf,
-                 unsigned long long *__restrict__ ghist, unsigned long long *__restrict__ gdescents) {
+                 unsigned long long *__restrict__ ghist, unsigned long long *__restrict__ gdescents,
+                 unsigned long long *__restrict__ gor, const Compaction cmp, typename Rec<ES>::type *__restrict__ cout) {
 	using R = typename Rec<ES>::type;
 	using KT = std::conditional_t<(KB > 4), unsigned long long, uint32_t>;
 	constexpr int VEC = 16 / ES;
@@ -137,6 +146,13 @@ histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_
 	const uint32_t inc = HistSmem<KB>::kPacked ? (1u << (lane & 16u)) : 1u;
 
 	uint32_t descents = 0;
+	KT acc_or = 0, acc_nand = 0; // which bits of the derived key vary over the input (key compaction)
+	auto derive = [&](const R &r) -> KT {
+		KT k = derive_fast<ES, KT>(r, xf);
+		if constexpr (COMPACT)
+			k = compact_key<KT>(k, cmp);
+		return k;
+	};
 	const uint4 *vsrc = reinterpret_cast<const uint4 *>(src + head);
 	const size_t stride = (size_t)gridDim.x * kHistThreads;
 	// CTA-uniform trip count so that the flush barrier is reached by every thread.
@@ -163,17 +179,22 @@ histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_
 			const R *e = reinterpret_cast<const R *>(&q[u]);
 #pragma unroll
 			for (int j = 0; j < VEC; ++j)
-				k[j] = derive_fast<ES, KT>(e[j], xf);
+				k[j] = derive(e[j]);
 			// successor of this vector's last record: next lane's first key, or a scalar load
 			KT nxt = __shfl_down_sync(0xFFFFFFFFu, k[0], 1);
 			const size_t next_idx = head + (v + 1) * VEC;
 			const bool have_next = live && next_idx < n;
 			if ((lane == 31 || v + 1 >= n_vec) && have_next)
-				nxt = derive_fast<ES, KT>(src[next_idx], xf);
+				nxt = derive(src[next_idx]);
 			if (live) {
 #pragma unroll
-				for (int j = 0; j < VEC; ++j)
+				for (int j = 0; j < VEC; ++j) {
 					hist_one<KB, KT>(lane_base, k[j], inc);
+					acc_or |= k[j];
+					acc_nand |= ~k[j];
+					if constexpr (COMPACT && ES <= 8)
+						cout[head + v * VEC + j] = (R)k[j];
+				}
 #pragma unroll
 				for (int j = 0; j + 1 < VEC; ++j)
 					descents += k[j] > k[j + 1];
@@ -197,16 +218,31 @@ histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_
 		const size_t extra = head + (n - tail0);
 		for (size_t t = tid; t < extra; t += kHistThreads) {
 			const size_t i = t < head ? t : tail0 + (t - head);
-			const KT k = derive_fast<ES, KT>(src[i], xf);
+			const KT k = derive(src[i]);
 			hist_one<KB, KT>(lane_base, k, inc);
+			acc_or |= k;
+			acc_nand |= ~k;
+			if constexpr (COMPACT && ES <= 8)
+				cout[i] = (R)k;
 			if (i + 1 < n)
-				descents += k > derive_fast<ES, KT>(src[i + 1], xf);
+				descents += k > derive(src[i + 1]);
 		}
 	}
 
 	descents = __reduce_add_sync(0xFFFFFFFFu, descents);
 	if (lane == 0 && descents)
 		atomicAdd(&s_desc, descents);
+	if constexpr (!COMPACT) {
+		unsigned long long o = (unsigned long long)acc_or, na = (unsigned long long)(KT)acc_nand;
+		for (int s_ = 16; s_; s_ >>= 1) {
+			o |= __shfl_xor_sync(0xFFFFFFFFu, o, s_);
+			na |= __shfl_xor_sync(0xFFFFFFFFu, na, s_);
+		}
+		if (lane == 0) {
+			atomicOr(&gor[0], o);
+			atomicOr(&gor[1], na);
+		}
+	}
 	__syncthreads();
 	hist_flush<KB>(sh, ghist);
 	if (tid == 0 && s_desc)
@@ -259,18 +295,20 @@ setup_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, KeyDesc k
 		}
 		ctl.pad = 0;
 		ctl.n = n;
+		ctl.key_or = ws->key_or;
+		ctl.key_nand = ws->key_nand & width_mask(kd.key_bytes);
 		ws->ctl = ctl;
 		if (host_ctl != nullptr)
 			*host_ctl = ctl; // mapped pinned memory: the host reads it after the stream has drained
 	}
 }
 
-template <int ES, int KB>
+template <int ES, int KB, bool COMPACT>
 cudaError_t launch_hist_t(const void *src, size_t n, const KeyDesc &kd, WsHead *ws, int num_sms,
-                          cudaStream_t st) {
+                          cudaStream_t st, const Compaction *cmp, void *cout) {
 	using R = typename Rec<ES>::type;
 	constexpr int VEC = 16 / ES;
-	auto kern = histogram_kernel<ES, KB>;
+	auto kern = histogram_kernel<ES, KB, COMPACT>;
 	static bool configured[64] = {}; // per device; benign race: setting the attribute is idempotent
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -290,35 +328,78 @@ cudaError_t launch_hist_t(const void *src, size_t n, const KeyDesc &kd, WsHead *
 	int grid = (int)(want < (size_t)num_sms ? (want ? want : 1) : (size_t)num_sms);
 	using KT = std::conditional_t<(KB > 4), unsigned long long, uint32_t>;
 	kern<<<grid, kHistThreads, HistSmem<KB>::kBytes, st>>>(static_cast<const R *>(src), n, head, n_vec,
-	                                                      make_xform<KT>(kd), ws->hist, &ws->descents);
+	                                                      make_xform<KT>(kd), ws->hist, &ws->descents, &ws->key_or,
+	                                                      cmp ? *cmp : Compaction{}, static_cast<R *>(cout));
 	count_launch();
 	return cudaGetLastError();
 }
 
 template <int ES>
 cudaError_t launch_hist_es(const void *src, size_t n, const KeyDesc &kd, WsHead *ws, int num_sms,
-                           cudaStream_t st) {
+                           cudaStream_t st, const Compaction *cmp, void *cout) {
+	if (cmp != nullptr) { // compaction: keys-only records of 4 or 8 bytes
+		if constexpr (ES == 4)
+			if (kd.key_bytes == 4)
+				return launch_hist_t<4, 4, true>(src, n, kd, ws, num_sms, st, cmp, cout);
+		if constexpr (ES == 8)
+			if (kd.key_bytes == 8)
+				return launch_hist_t<8, 8, true>(src, n, kd, ws, num_sms, st, cmp, cout);
+		return cudaErrorInvalidValue;
+	}
 	switch (kd.key_bytes) {
-	case 1: return launch_hist_t<ES, 1>(src, n, kd, ws, num_sms, st);
-	case 2: if constexpr (ES >= 2) return launch_hist_t<ES, 2>(src, n, kd, ws, num_sms, st); break;
-	case 4: if constexpr (ES >= 4) return launch_hist_t<ES, 4>(src, n, kd, ws, num_sms, st); break;
-	case 8: if constexpr (ES >= 8) return launch_hist_t<ES, 8>(src, n, kd, ws, num_sms, st); break;
+	case 1: return launch_hist_t<ES, 1, false>(src, n, kd, ws, num_sms, st, nullptr, nullptr);
+	case 2: if constexpr (ES >= 2) return launch_hist_t<ES, 2, false>(src, n, kd, ws, num_sms, st, nullptr, nullptr); break;
+	case 4: if constexpr (ES >= 4) return launch_hist_t<ES, 4, false>(src, n, kd, ws, num_sms, st, nullptr, nullptr); break;
+	case 8: if constexpr (ES >= 8) return launch_hist_t<ES, 8, false>(src, n, kd, ws, num_sms, st, nullptr, nullptr); break;
 	}
 	return cudaErrorInvalidValue;
+}
+
+// compacted keys -> original keys: PDEP over the runs, constant bits, inverse key derivation
+template <typename K>
+__global__ void expand_keys_kernel(const K *__restrict__ in, K *__restrict__ out, size_t n, KeyDesc kd, Compaction c) {
+	const unsigned long long m = width_mask(kd.key_bytes), top = 1ULL << (8u * kd.key_bytes - 1u);
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const unsigned long long v = (unsigned long long)in[i];
+		unsigned long long k = c.const_bits;
+		for (uint32_t r = 0; r < c.nruns; ++r)
+			k |= ((v >> c.dst_shift[r]) & ((1ULL << c.width[r]) - 1ULL)) << c.src_shift[r];
+		// inverse of derive_key (rsx_device.cuh): complement, then undo the sign / float flip
+		if (kd.invert)
+			k = ~k & m;
+		if (kd.kdf_kind == RSX_KDF_SIGNED)
+			k ^= top;
+		else if (kd.kdf_kind == RSX_KDF_FLOAT)
+			k ^= (k & top) ? top : m; // derived top bit set <=> the float was non-negative
+		out[i] = (K)k;
+	}
 }
 
 } // namespace
 
 cudaError_t launch_histogram(const void *src, size_t n, uint32_t record_bytes, const KeyDesc &kd,
-                             WsHead *ws, int num_sms, cudaStream_t st) {
+                             WsHead *ws, int num_sms, cudaStream_t st, const Compaction *cmp, void *compact_out) {
 	switch (record_bytes) {
-	case 1: return launch_hist_es<1>(src, n, kd, ws, num_sms, st);
-	case 2: return launch_hist_es<2>(src, n, kd, ws, num_sms, st);
-	case 4: return launch_hist_es<4>(src, n, kd, ws, num_sms, st);
-	case 8: return launch_hist_es<8>(src, n, kd, ws, num_sms, st);
-	case 16: return launch_hist_es<16>(src, n, kd, ws, num_sms, st);
+	case 1: return launch_hist_es<1>(src, n, kd, ws, num_sms, st, cmp, compact_out);
+	case 2: return launch_hist_es<2>(src, n, kd, ws, num_sms, st, cmp, compact_out);
+	case 4: return launch_hist_es<4>(src, n, kd, ws, num_sms, st, cmp, compact_out);
+	case 8: return launch_hist_es<8>(src, n, kd, ws, num_sms, st, cmp, compact_out);
+	case 16: return launch_hist_es<16>(src, n, kd, ws, num_sms, st, cmp, compact_out);
 	}
 	return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_expand_keys(const void *in, void *out, size_t n, const KeyDesc &kd, const Compaction &cmp,
+                               int num_sms, cudaStream_t st) {
+	const int g = (int)std::min<size_t>((n + 255) / 256, (size_t)num_sms * 16);
+	if (kd.key_bytes == 4)
+		expand_keys_kernel<<<g, 256, 0, st>>>(static_cast<const uint32_t *>(in), static_cast<uint32_t *>(out), n, kd, cmp);
+	else if (kd.key_bytes == 8)
+		expand_keys_kernel<<<g, 256, 0, st>>>(static_cast<const unsigned long long *>(in), static_cast<unsigned long long *>(out), n, kd, cmp);
+	else
+		return cudaErrorInvalidValue;
+	count_launch();
+	return cudaGetLastError();
 }
 
 cudaError_t launch_setup(const void *src, size_t n, uint32_t record_bytes, const KeyDesc &kd,

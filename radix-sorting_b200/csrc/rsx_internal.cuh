@@ -35,6 +35,21 @@ struct Ctl {
 	uint32_t ordinal[kMaxCols];     // index of column c among the live columns (if live)
 	uint32_t pad;
 	uint64_t n;
+	// OR of all derived keys and OR of their complements (K1): bit b varies over the input iff it
+	// is set in both.  The host reads them to decide on key compaction (README.md:716-758).
+	unsigned long long key_or, key_nand;
+};
+
+// Key compaction (the reference README's "future work", README.md:716-758): bits of the derived key
+// that are the same in every input key cannot influence the order, so the bits that DO vary are
+// gathered (a software PEXT over <= kMaxRuns runs of contiguous bits) into a narrower key that
+// needs fewer 8-bit passes; the last step scatters them back (PDEP) and restores the constant bits.
+constexpr int kMaxRuns = 8;
+struct Compaction {
+	uint32_t nruns;                       // 0: no compaction
+	uint32_t src_shift[kMaxRuns], width[kMaxRuns], dst_shift[kMaxRuns];
+	unsigned long long const_bits;        // derived-key bits outside the runs (all constant)
+	uint32_t bits;                        // total width of the compacted key
 };
 
 // Fixed-size head of the workspace.  Everything that must be zero before a sort comes first.
@@ -42,7 +57,8 @@ struct WsHead {
 	unsigned long long hist[kMaxCols * kBins]; // raw digit counts per column (zeroed)
 	unsigned long long descents;               // #i: kdf(a[i]) > kdf(a[i+1])       (zeroed)
 	unsigned int tickets[kMaxCols];            // tile tickets, one per column      (zeroed)
-	unsigned int pad0[6];
+	unsigned long long key_or, key_nand;       // see Ctl                            (zeroed)
+	unsigned int pad0[2];
 	// -- not zeroed below --
 	unsigned long long offs[kMaxCols * kBins]; // exclusive scan per column (radix_sort.hpp:72-80)
 	Ctl ctl;
@@ -74,8 +90,14 @@ struct PassGeometry {
 
 // ---- launchers (each returns the cudaError_t of the launch) ---------------------------------
 
+// compact_out != nullptr (keys-only records): histogram the COMPACTED derived keys and write them
+// to compact_out (record-sized unsigned values), see Compaction.
 cudaError_t launch_histogram(const void *src, size_t n, uint32_t record_bytes, const KeyDesc &kd,
-                             WsHead *ws, int num_sms, cudaStream_t st);
+                             WsHead *ws, int num_sms, cudaStream_t st, const Compaction *cmp = nullptr,
+                             void *compact_out = nullptr);
+// compacted keys -> original keys (PDEP + constant bits + inverse key derivation); in == out allowed
+cudaError_t launch_expand_keys(const void *in, void *out, size_t n, const KeyDesc &kd, const Compaction &cmp,
+                               int num_sms, cudaStream_t st);
 
 // host_ctl: mapped pinned mirror of ws->ctl (may be null)
 cudaError_t launch_setup(const void *src, size_t n, uint32_t record_bytes, const KeyDesc &kd,

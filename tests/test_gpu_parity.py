@@ -509,6 +509,53 @@ def test_records_of_any_size(rsx, torch, oracle, tname, n, dist, mask):
         assert res.numpy().tobytes() == want.tobytes()
 
 
+@pytest.mark.parametrize("tname,mask,orv,ncols,cpasses", [
+    ("u32", 0x0F0F0F0F, 0, 4, 2),                        # 16 varying bits in 4 byte columns -> 2 passes, result back in src
+    ("u32", 0x0F0F0F0F, 0xA0500000, 4, 2),                # constant ONE bits between the runs
+    ("u64", 0x0F0F0F0F0F0F0F0F, 0, 8, 4),
+    ("u64", 0x000F0F0F0F0F0F0F, 0, 7, 4),                 # odd column count: the reference returns aux
+    ("u64", 0x1F1F1F1F1F1F1F1F, 0, 8, 5),                 # 40 bits -> 5 passes, data ends where the reference wants it
+    ("i32", 0x0F0F0F0F, 0, 4, 2), ("i64", 0x0303030303030303, 0x8000000000000000, 8, 2),
+    ("f32", 0x3F0F0F0F, 0, 4, 3), ("f64", 0x0F0F0F0F0F0F0F0F, 0x8000000000000000, 8, 4),  # positive and negative floats
+    ("u32", 0x00FF0F0F, 0, 3, 0),                         # would save one pass only: not compacted
+    ("u32", 0x55555555, 0, 4, 2),                         # 16 single-bit runs merged into <= 8 runs
+])
+@pytest.mark.parametrize("desc", [False, True], ids=["asc", "desc"])
+def test_key_compaction(rsx, torch, oracle, tname, mask, orv, ncols, cpasses, desc):
+    """N4 (README.md:716-758): key bits that are constant over the input cannot influence the order;
+    the varying bits are gathered into a narrower key and sorted in fewer passes.  Output, live
+    column count and returned buffer stay exactly the reference's."""
+    t = TYPES[tname]
+    n = 600_007
+    data = make_input(tname, n, 23, "uniform", mask, orv)
+    try:
+        assert rsx.lib().rsx_set_option(b"compact_min_n", 1000) == 0
+        out, rep, in_aux = gpu_sort(rsx, torch, tname, data, descending=desc)
+    finally:
+        rsx.lib().rsx_set_option(b"compact_min_n", 1 << 24)
+    want, orep, _ = oracle.radix_sort(data, t.layout(descending=desc))
+    assert rep.compacted_passes == cpasses, (rep.compacted_passes, cpasses)
+    assert rep.ncols == orep.ncols == ncols and rep.result_in_aux == orep.result_in_aux == int(in_aux)
+    assert out.tobytes() == want.tobytes()
+
+
+def test_key_compaction_leaves_full_entropy_keys_alone(rsx, torch):
+    """and3 keys are low-entropy but no bit is constant: nothing to compact; 20 M nibble-masked keys
+    cross the default threshold and are."""
+    n = 20_000_003
+    for dist, mask, expect in (("and3", (1 << 64) - 1, 0), ("uniform", 0x0F0F0F0F, 2)):
+        src = torch.empty(n, dtype=torch.int32, device="cuda")
+        aux = torch.empty_like(src)
+        rsx.fill_keys(src, seed=5, dist=dist, mask=mask)
+        kf = rsx.KeyFunc(rsx.KDF_UNSIGNED)
+        _, s0, x0 = rsx.verify(src, kf)
+        rep = rsx.RsxReport()
+        res = rsx.radix_sort(src, aux, None, kf, report=rep)
+        d1, s1, x1 = rsx.verify(res, kf)
+        assert d1 == 0 and (s1, x1) == (s0, x0)
+        assert rep.compacted_passes == expect and rep.ncols == 4 and res.data_ptr() == src.data_ptr()
+
+
 def test_multipass_composite_key_like_listing5(rsx, torch, oracle):
     """radix_sort_u64_multipass.c:117-118 sorts a 64-bit key with two stable 32-bit sorts (low half,
     then high half).  The same composition through key_offset/key_bytes windows must equal one
