@@ -301,7 +301,8 @@ def bench_single(args, rsx, torch, workload, dev, steps, warmup, do_e2e, do_cpu)
 
     # ---- roofline of the dominant kernel: the scatter pass (K3) --------------------------------
     peak, peak_src = measured_peak()
-    pass_ms = [p[2 + c] for p in profs for c in range(kb) if len(p) > 2 + c and p[2 + c] > 0 and (rep.live_mask >> c) & 1]
+    ran = (lambda c: c < rep.compacted_passes) if rep.compacted_passes else (lambda c: (rep.live_mask >> c) & 1)
+    pass_ms = [p[2 + c] for p in profs for c in range(kb) if len(p) > 2 + c and p[2 + c] > 0 and ran(c)]
     hist_ms = [p[0] for p in profs if p]
     avg_pass = sum(pass_ms) / len(pass_ms)
     alg_bytes_pass = 2 * n * kb  # read n records + write n records (2K per key per pass)
@@ -319,7 +320,8 @@ def bench_single(args, rsx, torch, workload, dev, steps, warmup, do_e2e, do_cpu)
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "traffic_source": traffic_src,
         "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_pass, "ms_per_launch": avg_pass,
-        "launches_timed": len(pass_ms), "share_of_step": avg_pass * passes / ms_per_step,
+        "launches_timed": len(pass_ms), "share_of_step": avg_pass * (rep.compacted_passes or passes) / ms_per_step,
+        "key_compaction_passes": int(rep.compacted_passes) or None,
         "histogram_kernel": {"ms": hist_avg, "alg_bytes": n * kb, "achieved": n * kb / (hist_avg * 1e-3) / 1e9,
                              "frac": n * kb / (hist_avg * 1e-3) / 1e9 / peak},
         "whole_sort": {"alg_bytes": alg_bytes_sort, "achieved": alg_bytes_sort / (ms_per_step * 1e-3) / 1e9,

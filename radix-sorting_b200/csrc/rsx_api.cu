@@ -706,6 +706,7 @@ static bool plan_compaction(const Ctl &c, const KeyDesc &kd, Compaction *out) {
 		k.src_shift[i] = runs[i].lo;
 		k.width[i] = runs[i].hi - runs[i].lo;
 		k.dst_shift[i] = at;
+		k.wmask[i] = k.width[i] >= 64 ? ~0ULL : ((1ULL << k.width[i]) - 1ULL);
 		at += k.width[i];
 		covered |= (k.width[i] >= 64 ? ~0ULL : ((1ULL << k.width[i]) - 1ULL)) << runs[i].lo;
 	}

@@ -70,17 +70,18 @@ __device__ __forceinline__ KT derive_fast(const typename Rec<ES>::type &r, const
 	return k;
 }
 
-template <typename KT> __device__ __forceinline__ KT compact_key(KT k, const Compaction &c) {
+template <typename KT, int NR> __device__ __forceinline__ KT compact_key(KT k, const Compaction &c) {
 	KT out = 0;
-	for (uint32_t i = 0; i < c.nruns; ++i)
-		out |= ((k >> c.src_shift[i]) & (KT)((1ULL << c.width[i]) - 1ULL)) << c.dst_shift[i];
+#pragma unroll // compile-time indices: the run table stays in the constant bank (a runtime index spills it to local memory)
+	for (int i = 0; i < NR; ++i)
+		out |= ((k >> c.src_shift[i]) & (KT)c.wmask[i]) << c.dst_shift[i]; // unused runs have wmask 0
 	return out;
 }
 
 // One increment per column.  `lane_base` already contains the lane's bank offset, so each
 // digit costs a shift, a mask, an add and the shared atomic.
 template <int KB, typename KT>
-__device__ __forceinline__ void hist_one(unsigned char *lane_base, KT key, uint32_t inc) {
+__device__ __forceinline__ void hist_one(unsigned char *lane_base, KT key, uint32_t inc, int cols = KB) {
 	constexpr bool kPacked = HistSmem<KB>::kPacked;
 	constexpr uint32_t kColBytes = kPacked ? kBins * 64u : kBins * 128u; // bytes per column
 	constexpr uint32_t kSh = kPacked ? 6u : 7u;                          // bytes per bin = 1 << kSh
@@ -94,7 +95,8 @@ __device__ __forceinline__ void hist_one(unsigned char *lane_base, KT key, uint3
 		}
 		const int cc = c & 3;
 		const uint32_t off = cc == 0 ? (half << kSh) & kMaskOff : (half >> (8 * cc - kSh)) & kMaskOff;
-		atomicAdd(reinterpret_cast<uint32_t *>(lane_base + c * kColBytes + off), inc);
+		if (c < cols) // compacted keys: the columns above the compacted width are all zero, counted wholesale
+			atomicAdd(reinterpret_cast<uint32_t *>(lane_base + c * kColBytes + off), inc);
 	}
 }
 
@@ -121,7 +123,8 @@ __device__ __forceinline__ void hist_flush(uint32_t *sh, unsigned long long *ghi
 	}
 }
 
-template <int ES, int KB, bool COMPACT>
+// COMPACT: 0 = off, else the number of runs the software PEXT is unrolled for (2, 4 or 8)
+template <int ES, int KB, int COMPACT>
 __global__ void __launch_bounds__(kHistThreads, 1)
 histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_t head, size_t n_vec,
                  KeyXform<std::conditional_t<(KB > 4), unsigned long long, uint32_t>> xf,
@@ -146,11 +149,13 @@ histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_
 	const uint32_t inc = HistSmem<KB>::kPacked ? (1u << (lane & 16u)) : 1u;
 
 	uint32_t descents = 0;
+	const int hcols = COMPACT ? (int)(cmp.bits + 7) / 8 : KB;
+	const bool vec_out = COMPACT != 0 && ES <= 8 && (reinterpret_cast<uintptr_t>(cout + head) & 15) == 0;
 	KT acc_or = 0, acc_nand = 0; // which bits of the derived key vary over the input (key compaction)
 	auto derive = [&](const R &r) -> KT {
 		KT k = derive_fast<ES, KT>(r, xf);
 		if constexpr (COMPACT)
-			k = compact_key<KT>(k, cmp);
+			k = compact_key<KT, COMPACT>(k, cmp);
 		return k;
 	};
 	const uint4 *vsrc = reinterpret_cast<const uint4 *>(src + head);
@@ -189,11 +194,24 @@ histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_
 			if (live) {
 #pragma unroll
 				for (int j = 0; j < VEC; ++j) {
-					hist_one<KB, KT>(lane_base, k[j], inc);
-					acc_or |= k[j];
-					acc_nand |= ~k[j];
-					if constexpr (COMPACT && ES <= 8)
-						cout[head + v * VEC + j] = (R)k[j];
+					hist_one<KB, KT>(lane_base, k[j], inc, hcols);
+					if constexpr (!COMPACT) {
+						acc_or |= k[j];
+						acc_nand |= ~k[j];
+					}
+				}
+				if constexpr (COMPACT != 0 && ES <= 8) {
+					if (vec_out) { // one 16-byte store per input vector
+						R o[VEC];
+#pragma unroll
+						for (int j = 0; j < VEC; ++j)
+							o[j] = (R)k[j];
+						reinterpret_cast<uint4 *>(cout + head)[v] = *reinterpret_cast<const uint4 *>(o);
+					} else {
+#pragma unroll
+						for (int j = 0; j < VEC; ++j)
+							cout[head + v * VEC + j] = (R)k[j];
+					}
 				}
 #pragma unroll
 				for (int j = 0; j + 1 < VEC; ++j)
@@ -219,10 +237,10 @@ histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_
 		for (size_t t = tid; t < extra; t += kHistThreads) {
 			const size_t i = t < head ? t : tail0 + (t - head);
 			const KT k = derive(src[i]);
-			hist_one<KB, KT>(lane_base, k, inc);
+			hist_one<KB, KT>(lane_base, k, inc, hcols);
 			acc_or |= k;
 			acc_nand |= ~k;
-			if constexpr (COMPACT && ES <= 8)
+			if constexpr (COMPACT != 0 && ES <= 8)
 				cout[i] = (R)k;
 			if (i + 1 < n)
 				descents += k > derive(src[i + 1]);
@@ -247,6 +265,10 @@ histogram_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, size_
 	hist_flush<KB>(sh, ghist);
 	if (tid == 0 && s_desc)
 		atomicAdd(gdescents, (unsigned long long)s_desc);
+	if constexpr (COMPACT) {
+		if (blockIdx.x == 0 && tid < KB && (int)tid >= hcols)
+			atomicAdd(&ghist[tid * kBins], (unsigned long long)n); // every key has digit 0 in this column
+	}
 }
 
 // K2: one CTA, 256 threads; thread d owns bin d of every column.
@@ -303,7 +325,7 @@ setup_kernel(const typename Rec<ES>::type *__restrict__ src, size_t n, KeyDesc k
 	}
 }
 
-template <int ES, int KB, bool COMPACT>
+template <int ES, int KB, int COMPACT>
 cudaError_t launch_hist_t(const void *src, size_t n, const KeyDesc &kd, WsHead *ws, int num_sms,
                           cudaStream_t st, const Compaction *cmp, void *cout) {
 	using R = typename Rec<ES>::type;
@@ -338,41 +360,70 @@ template <int ES>
 cudaError_t launch_hist_es(const void *src, size_t n, const KeyDesc &kd, WsHead *ws, int num_sms,
                            cudaStream_t st, const Compaction *cmp, void *cout) {
 	if (cmp != nullptr) { // compaction: keys-only records of 4 or 8 bytes
-		if constexpr (ES == 4)
-			if (kd.key_bytes == 4)
-				return launch_hist_t<4, 4, true>(src, n, kd, ws, num_sms, st, cmp, cout);
-		if constexpr (ES == 8)
-			if (kd.key_bytes == 8)
-				return launch_hist_t<8, 8, true>(src, n, kd, ws, num_sms, st, cmp, cout);
+		if constexpr (ES == 4 || ES == 8) {
+			if (kd.key_bytes == ES) {
+				if (cmp->nruns <= 2)
+					return launch_hist_t<ES, ES, 2>(src, n, kd, ws, num_sms, st, cmp, cout);
+				if (cmp->nruns <= 4)
+					return launch_hist_t<ES, ES, 4>(src, n, kd, ws, num_sms, st, cmp, cout);
+				return launch_hist_t<ES, ES, 8>(src, n, kd, ws, num_sms, st, cmp, cout);
+			}
+		}
 		return cudaErrorInvalidValue;
 	}
 	switch (kd.key_bytes) {
-	case 1: return launch_hist_t<ES, 1, false>(src, n, kd, ws, num_sms, st, nullptr, nullptr);
-	case 2: if constexpr (ES >= 2) return launch_hist_t<ES, 2, false>(src, n, kd, ws, num_sms, st, nullptr, nullptr); break;
-	case 4: if constexpr (ES >= 4) return launch_hist_t<ES, 4, false>(src, n, kd, ws, num_sms, st, nullptr, nullptr); break;
-	case 8: if constexpr (ES >= 8) return launch_hist_t<ES, 8, false>(src, n, kd, ws, num_sms, st, nullptr, nullptr); break;
+	case 1: return launch_hist_t<ES, 1, 0>(src, n, kd, ws, num_sms, st, nullptr, nullptr);
+	case 2: if constexpr (ES >= 2) return launch_hist_t<ES, 2, 0>(src, n, kd, ws, num_sms, st, nullptr, nullptr); break;
+	case 4: if constexpr (ES >= 4) return launch_hist_t<ES, 4, 0>(src, n, kd, ws, num_sms, st, nullptr, nullptr); break;
+	case 8: if constexpr (ES >= 8) return launch_hist_t<ES, 8, 0>(src, n, kd, ws, num_sms, st, nullptr, nullptr); break;
 	}
 	return cudaErrorInvalidValue;
 }
 
-// compacted keys -> original keys: PDEP over the runs, constant bits, inverse key derivation
+// compacted keys -> original keys: PDEP over the runs, constant bits, inverse key derivation.
+// 16-byte accesses, two vectors in flight per thread (a 4-byte-per-thread version ran at half the
+// HBM rate: too few bytes in flight).
+template <typename K> __device__ __forceinline__ K expand_one(K cv, const KeyDesc &kd, const Compaction &c, unsigned long long m,
+                                                              unsigned long long top) {
+	const unsigned long long v = (unsigned long long)cv;
+	unsigned long long k = c.const_bits;
+#pragma unroll
+	for (int r = 0; r < kMaxRuns; ++r)
+		k |= ((v >> c.dst_shift[r]) & c.wmask[r]) << c.src_shift[r]; // unused runs have wmask 0
+	// inverse of derive_key (rsx_device.cuh): complement, then undo the sign / float flip
+	if (kd.invert)
+		k = ~k & m;
+	if (kd.kdf_kind == RSX_KDF_SIGNED)
+		k ^= top;
+	else if (kd.kdf_kind == RSX_KDF_FLOAT)
+		k ^= (k & top) ? top : m; // derived top bit set <=> the float was non-negative
+	return (K)k;
+}
+
 template <typename K>
 __global__ void expand_keys_kernel(const K *__restrict__ in, K *__restrict__ out, size_t n, KeyDesc kd, Compaction c) {
+	constexpr int VEC = 16 / (int)sizeof(K);
 	const unsigned long long m = width_mask(kd.key_bytes), top = 1ULL << (8u * kd.key_bytes - 1u);
-	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-		const unsigned long long v = (unsigned long long)in[i];
-		unsigned long long k = c.const_bits;
-		for (uint32_t r = 0; r < c.nruns; ++r)
-			k |= ((v >> c.dst_shift[r]) & ((1ULL << c.width[r]) - 1ULL)) << c.src_shift[r];
-		// inverse of derive_key (rsx_device.cuh): complement, then undo the sign / float flip
-		if (kd.invert)
-			k = ~k & m;
-		if (kd.kdf_kind == RSX_KDF_SIGNED)
-			k ^= top;
-		else if (kd.kdf_kind == RSX_KDF_FLOAT)
-			k ^= (k & top) ? top : m; // derived top bit set <=> the float was non-negative
-		out[i] = (K)k;
+	const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+	const size_t nv = aligned ? n / VEC : 0;
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	const uint4 *vin = reinterpret_cast<const uint4 *>(in);
+	uint4 *vout = reinterpret_cast<uint4 *>(out);
+	for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += 2 * stride) {
+		const size_t v2 = v + stride;
+		uint4 a = vin[v], b = v2 < nv ? vin[v2] : make_uint4(0, 0, 0, 0);
+		K *ka = reinterpret_cast<K *>(&a), *kb = reinterpret_cast<K *>(&b);
+#pragma unroll
+		for (int j = 0; j < VEC; ++j) {
+			ka[j] = expand_one<K>(ka[j], kd, c, m, top);
+			kb[j] = expand_one<K>(kb[j], kd, c, m, top);
+		}
+		vout[v] = a;
+		if (v2 < nv)
+			vout[v2] = b;
 	}
+	for (size_t i = nv * VEC + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+		out[i] = expand_one<K>(in[i], kd, c, m, top);
 }
 
 } // namespace
@@ -391,7 +442,7 @@ cudaError_t launch_histogram(const void *src, size_t n, uint32_t record_bytes, c
 
 cudaError_t launch_expand_keys(const void *in, void *out, size_t n, const KeyDesc &kd, const Compaction &cmp,
                                int num_sms, cudaStream_t st) {
-	const int g = (int)std::min<size_t>((n + 255) / 256, (size_t)num_sms * 16);
+	const int g = (int)std::min<size_t>((n / 8 + 255) / 256 + 1, (size_t)num_sms * 8);
 	if (kd.key_bytes == 4)
 		expand_keys_kernel<<<g, 256, 0, st>>>(static_cast<const uint32_t *>(in), static_cast<uint32_t *>(out), n, kd, cmp);
 	else if (kd.key_bytes == 8)

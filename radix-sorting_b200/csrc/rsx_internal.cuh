@@ -48,6 +48,7 @@ constexpr int kMaxRuns = 8;
 struct Compaction {
 	uint32_t nruns;                       // 0: no compaction
 	uint32_t src_shift[kMaxRuns], width[kMaxRuns], dst_shift[kMaxRuns];
+	unsigned long long wmask[kMaxRuns];   // (1 << width) - 1; 0 for unused runs (they then contribute nothing)
 	unsigned long long const_bits;        // derived-key bits outside the runs (all constant)
 	uint32_t bits;                        // total width of the compacted key
 };

@@ -516,9 +516,11 @@ def test_records_of_any_size(rsx, torch, oracle, tname, n, dist, mask):
     ("u64", 0x000F0F0F0F0F0F0F, 0, 7, 4),                 # odd column count: the reference returns aux
     ("u64", 0x1F1F1F1F1F1F1F1F, 0, 8, 5),                 # 40 bits -> 5 passes, data ends where the reference wants it
     ("i32", 0x0F0F0F0F, 0, 4, 2), ("i64", 0x0303030303030303, 0x8000000000000000, 8, 2),
-    ("f32", 0x3F0F0F0F, 0, 4, 3), ("f64", 0x0F0F0F0F0F0F0F0F, 0x8000000000000000, 8, 4),  # positive and negative floats
+    ("f32", 0x0F0F0F0F, 0, 4, 2), ("f64", 0x0F0F0F0F0F0F0F0F, 0x8000000000000000, 8, 4),  # positive and negative floats
+    ("f32", 0x3F0F0F0F, 0, 4, 0),                         # 18 varying bits: 3 passes would save only one
     ("u32", 0x00FF0F0F, 0, 3, 0),                         # would save one pass only: not compacted
-    ("u32", 0x55555555, 0, 4, 2),                         # 16 single-bit runs merged into <= 8 runs
+    ("u64", 0x0303030303033333, 0, 8, 3),                 # 10 runs of 2 bits: the two closest pairs are merged (<= 8 runs, 24 bits)
+    ("u32", 0x55555555, 0, 4, 0),                         # 16 single-bit runs: merged runs span 24 bits, only one pass saved
 ])
 @pytest.mark.parametrize("desc", [False, True], ids=["asc", "desc"])
 def test_key_compaction(rsx, torch, oracle, tname, mask, orv, ncols, cpasses, desc):
