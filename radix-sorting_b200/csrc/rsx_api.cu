@@ -713,8 +713,10 @@ static bool plan_compaction(const Ctl &c, const KeyDesc &kd, Compaction *out) {
 	k.nruns = (uint32_t)nr;
 	k.bits = at;
 	k.const_bits = c.key_or & ~covered & m; // constant bits: set in every key or in none
+	// The compacting histogram + the expansion cost about as much as 1.5 (4-byte keys) to 1.8
+	// (8-byte keys) passes: compact only when clearly more passes are saved (profiles/r2_variants.md).
 	const uint32_t passes = (at + 7) / 8;
-	if (passes + 2 > c.ncols)
+	if (passes + (kd.key_bytes == 4 ? 3u : 2u) > c.ncols)
 		return false;
 	*out = k;
 	return true;
