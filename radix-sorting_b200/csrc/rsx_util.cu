@@ -255,11 +255,12 @@ cudaError_t launch_split_counts(const void *data, size_t n, uint32_t record_byte
 }
 
 cudaError_t launch_ticket_probe(unsigned long long *d_mismatch, int num_sms, cudaStream_t st) {
-	// ~20 M tickets per launch; the offline probe (tools/probe_atoms.cu) runs billions
+	// ~5 M tickets per launch, on every SM (0.3 ms in total, once per device); the offline probe
+	// (tools/probe_atoms.cu) runs billions
 	for (uint32_t mask : {0xFFu, 0x0Fu, 0x01u}) {
-		ticket_probe_kernel<0><<<num_sms, 512, 0, st>>>(d_mismatch, 16, mask);
-		ticket_probe_kernel<1><<<num_sms, 512, 0, st>>>(d_mismatch, 16, mask);
-		ticket_probe_kernel<2><<<num_sms, 512, 0, st>>>(d_mismatch, 16, mask);
+		ticket_probe_kernel<0><<<num_sms, 512, 0, st>>>(d_mismatch, 4, mask);
+		ticket_probe_kernel<1><<<num_sms, 512, 0, st>>>(d_mismatch, 4, mask);
+		ticket_probe_kernel<2><<<num_sms, 512, 0, st>>>(d_mismatch, 4, mask);
 	}
 	count_launch(9);
 	return cudaGetLastError();
