@@ -265,7 +265,7 @@ uint64_t rsx_total_kernel_launches(void); /* process-wide count, for bench.py's 
  * "query_rank_mode" returns the mode in effect (0 / 1).  "scatter_variant" (0..5) selects a tile
  * geometry used in tuning sweeps, "force_wide" (0/1) runs the n >= 2^30 (64-bit offset) kernels
  * at any n (tests).  "compact_min_n": key compaction is considered for keys-only sorts of at least
- * this many 4/8-byte keys (default 2^24; <= 0 disables it).  "profile" (0/1): bracket every kernel of rsx_sort / rsx_sort_rank with CUDA events on
+ * this many 4/8-byte keys (default 2^26: below that the extra stream wait costs more than compaction can save; <= 0 disables it).  "profile" (0/1): bracket every kernel of rsx_sort / rsx_sort_rank with CUDA events on
  * the launch stream so that per-kernel device times can be read back with rsx_get_profile
  * (bench.py's roofline leg; off by default because the extra events perturb nothing but are
  * not free). */

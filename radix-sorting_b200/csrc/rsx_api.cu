@@ -22,7 +22,7 @@ namespace rsx {
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<int> g_force_wide{0};
 static std::atomic<int> g_small_path{1};
-static std::atomic<long> g_compact_min_n{1L << 24}; // rsx_set_option("compact_min_n", n); <= 0 disables
+static std::atomic<long> g_compact_min_n{1L << 26}; // rsx_set_option("compact_min_n", n); <= 0 disables
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 namespace {

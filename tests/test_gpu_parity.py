@@ -535,7 +535,7 @@ def test_key_compaction(rsx, torch, oracle, tname, mask, orv, ncols, cpasses, de
         assert rsx.lib().rsx_set_option(b"compact_min_n", 1000) == 0
         out, rep, in_aux = gpu_sort(rsx, torch, tname, data, descending=desc)
     finally:
-        rsx.lib().rsx_set_option(b"compact_min_n", 1 << 24)
+        rsx.lib().rsx_set_option(b"compact_min_n", 1 << 26)
     want, orep, _ = oracle.radix_sort(data, t.layout(descending=desc))
     assert rep.compacted_passes == cpasses, (rep.compacted_passes, cpasses)
     assert rep.ncols == orep.ncols == ncols and rep.result_in_aux == orep.result_in_aux == int(in_aux)
@@ -543,9 +543,9 @@ def test_key_compaction(rsx, torch, oracle, tname, mask, orv, ncols, cpasses, de
 
 
 def test_key_compaction_leaves_full_entropy_keys_alone(rsx, torch):
-    """and3 keys are low-entropy but no bit is constant: nothing to compact; 20 M nibble-masked keys
-    cross the default threshold and are."""
-    n = 20_000_003
+    """and3 keys are low-entropy but no bit is constant: nothing to compact; 70 M masked keys with 6
+    varying bits cross the default threshold and are."""
+    n = 70_000_003
     for dist, mask, expect in (("and3", (1 << 64) - 1, 0), ("uniform", 0x03010103, 1)):
         src = torch.empty(n, dtype=torch.int32, device="cuda")
         aux = torch.empty_like(src)
