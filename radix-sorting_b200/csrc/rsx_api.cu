@@ -22,6 +22,7 @@ namespace rsx {
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<int> g_force_wide{0};
 static std::atomic<int> g_small_path{1};
+static std::atomic<int> g_fused_bulk{1}; // rsx_set_option("fused_bulk", 0/1): TMA bulk stores in the fused partition pass
 static std::atomic<long> g_compact_min_n{1L << 26}; // rsx_set_option("compact_min_n", n); <= 0 disables
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -514,6 +515,8 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
 	sp.dest_base = dest_base;
 	sp.owner = owner;
 	sp.ndest = (uint32_t)ndest;
+	// keys-only records: the order inside a (tile, destination) run is free -> TMA bulk stores
+	sp.unordered_runs = (dest_base != nullptr && record_bytes == kd.key_bytes && record_bytes < 16 && g_fused_bulk.load(std::memory_order_relaxed)) ? 1u : 0u;
 	sp.kd = kd;
 	sp.nsplit = (uint32_t)nsplit;
 	for (int j = 0; j < kMaxSplit; ++j)
@@ -603,6 +606,10 @@ int rsx_set_option(const char *name, long value) {
 	}
 	if (name && strcmp(name, "compact_min_n") == 0) { // key compaction for keys-only sorts of >= value keys; <= 0: never
 		g_compact_min_n.store(value > 0 ? value : (1L << 62));
+		return RSX_OK;
+	}
+	if (name && strcmp(name, "fused_bulk") == 0) { // A/B: keys-only fused passes store their runs with TMA bulk copies
+		g_fused_bulk.store(value ? 1 : 0);
 		return RSX_OK;
 	}
 	if (name && strcmp(name, "force_wide") == 0) { // tests: run the n >= 2^30 (64-bit offset) kernels at small n

@@ -63,6 +63,10 @@ struct ScatterParams {
 	const unsigned long long *dest_base; // device memory, one byte address per destination
 	const unsigned char *owner;          // device memory, 256 entries
 	uint32_t ndest;
+	// Keys-only records (the whole record is the key): equal records are indistinguishable, so the
+	// order INSIDE one (tile, destination) run is free -- its 16-byte-aligned body can then leave as
+	// ONE TMA bulk store (shared -> peer memory) instead of LSU stores.
+	uint32_t unordered_runs;
 	// Key-range routing (DIGIT_SPLIT): the "digit" of a record is the number of splitters that are
 	// <= its derived key, i.e. its destination among nsplit + 1 key ranges.
 	KeyDesc kd;
@@ -141,6 +145,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// TMA 1-D bulk store (shared -> global, possibly peer memory over NVLink), bulk-group completion
+__device__ __forceinline__ void bulk_s2g(unsigned long long dst, const void *src, uint32_t bytes) {
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
 	asm volatile("{\n"
 	             ".reg .pred P1;\n"
@@ -455,6 +468,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 			}
 		}
 		RSX_T(1);
+		if constexpr (FUSED) {
+			if (tid == 0 && p.unordered_runs)
+				bulk_wait_read(); // the previous tile's bulk stores have read the sorted buffer
+		}
 		__syncthreads(); // (A) all warp counters final
 		RSX_T(2);
 
@@ -673,6 +690,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		RSX_T(6);
 		if (tid == 0) // next ticket: claimed as late as possible (see above)
 			s_misc[0] = atomicAdd(p.ticket, 1u);
+		if constexpr (FUSED) {
+			if (p.unordered_runs)
+				fence_async_smem(); // the sorted tile (generic-proxy stores) becomes visible to the TMA
+		}
 		__syncthreads(); // (D) sorted tile + gadj complete; nobody reads the staging buffer any more
 		const uint32_t next_tile = s_misc[0];
 		if (tid == 0 && can_stage && next_tile < full_tiles)
@@ -686,6 +707,29 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 			// (708 vs 480 GB/s for 4-byte stores, tools/peer_bw.py).  The shared-memory side is then
 			// misaligned by a per-run constant: two aligned 16-byte loads + a funnel shift.
 			constexpr uint32_t G = ES >= 16 ? 1u : 16u / ES; // records per 16-byte chunk
+			if (p.unordered_runs && ES < 16) {
+				// Keys-only: per destination ONE bulk store of the largest body that is 16-byte aligned
+				// on both sides; the < 3 G records around it go out as scalar stores, the j-th left-over
+				// slot to the j-th left-over remote position (order inside the run is free).
+				for (uint32_t k = 0; k < p.ndest; ++k) {
+					const uint32_t beg = s_dstart[k], cnt = s_dcount[k];
+					const unsigned long long r0 = p.dest_base[k] + s_dexcl[k] * ES;
+					const uint32_t hs = (G - (beg & (G - 1))) & (G - 1);                    // slots to shared alignment
+					const uint32_t hr = (uint32_t)((G - ((r0 / ES) & (G - 1))) & (G - 1));  // records to remote alignment
+					const uint32_t hmax = hs > hr ? hs : hr;
+					const uint32_t L = cnt > hmax ? (cnt - hmax) / G * G : 0u;
+					if (tid == 0 && L)
+						bulk_s2g(r0 + (unsigned long long)hr * ES, s_rec + beg + hs, L * ES);
+					const uint32_t left = cnt - L;
+					if (tid < left) {
+						const uint32_t sl = tid < hs ? beg + tid : beg + hs + L + (tid - hs);
+						const uint32_t rl = tid < hr ? tid : hr + L + (tid - hr);
+						*reinterpret_cast<R *>(r0 + (unsigned long long)rl * ES) = s_rec[sl];
+					}
+				}
+				if (tid == 0)
+					bulk_commit();
+			} else
 			for (uint32_t k = 0; k < p.ndest; ++k) {
 				const uint32_t beg = s_dstart[k], end = beg + s_dcount[k];
 				const unsigned long long r0 = p.dest_base[k] + s_dexcl[k] * ES; // remote byte address of slot `beg`
@@ -758,6 +802,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		RSX_T(8);
 		tile = next_tile;
 		// the next iteration rewrites wh (read in step 4, fenced by D) and s_rec (fenced by A', C')
+	}
+	if constexpr (FUSED) {
+		if (tid == 0 && p.unordered_runs)
+			bulk_wait_all(); // every bulk store of this CTA has been written
 	}
 #ifdef RSX_PHASE_TIMING
 	if (tid == 0 && p.dbg) {
