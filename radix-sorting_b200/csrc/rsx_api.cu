@@ -1289,20 +1289,27 @@ int rsx_split_counts(const void *src, size_t n, const rsx_layout *layout, const 
 	if ((r = current_device(&dev)))
 		return r;
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
-	unsigned long long *d = nullptr, h[16] = {};
-	CU(cudaMalloc((void **)&d, 32 * sizeof(unsigned long long)));
-	cudaError_t e = cudaMemsetAsync(d, 0, 32 * sizeof(unsigned long long), st);
-	if (e == cudaSuccess)
-		e = cudaMemcpyAsync(d + 16, splitters, sizeof(uint64_t) * nsplit, cudaMemcpyHostToDevice, st);
-	if (e == cudaSuccess && n)
-		e = launch_split_counts(src, n, layout->record_bytes, kd, d + 16, (uint32_t)nsplit, d, g_dev[dev].num_sms, st);
-	if (e == cudaSuccess)
-		e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st);
-	if (e == cudaSuccess)
-		e = cudaStreamSynchronize(st);
-	cudaFree(d);
-	if (e != cudaSuccess)
-		return fail_cuda(e, "rsx_split_counts");
+	for (int j = 0; j <= nsplit; ++j)
+		counts_out[j] = 0;
+	if (n == 0)
+		return RSX_OK;
+	// the counters live in the (zeroed) head of the cached workspace: no allocation per call
+	rsx_layout l1 = *layout;
+	Plan P;
+	make_plan(P, 2, &l1, kd, 0);
+	Lease L;
+	if ((r = acquire(L, dev, P.total)))
+		return r;
+	L.enqueued(st);
+	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
+	unsigned long long h[16] = {};
+	CU(zero_workspace(P, wsp, st));
+	CU(launch_split_counts(src, n, layout->record_bytes, kd, reinterpret_cast<const unsigned long long *>(splitters),
+	                       (uint32_t)nsplit, ws->hist, g_dev[dev].num_sms, st));
+	CU(cudaMemcpyAsync(h, ws->hist, sizeof(h), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	L.drained();
 	for (int j = 0; j <= nsplit; ++j)
 		counts_out[j] = h[j];
 	return RSX_OK;
@@ -1367,18 +1374,22 @@ int rsx_verify(const void *data, size_t n, const rsx_layout *layout, uint64_t *d
 	if ((r = current_device(&dev)))
 		return r;
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
-	unsigned long long *d3 = nullptr, h3[3] = {0, 0, 0};
-	CU(cudaMalloc((void **)&d3, 3 * sizeof(unsigned long long)));
-	cudaError_t e = cudaMemsetAsync(d3, 0, 3 * sizeof(unsigned long long), st);
-	if (e == cudaSuccess && n)
-		e = launch_verify(data, n, layout->record_bytes, kd, d3, g_dev[dev].num_sms, st);
-	if (e == cudaSuccess)
-		e = cudaMemcpyAsync(h3, d3, sizeof(h3), cudaMemcpyDeviceToHost, st);
-	if (e == cudaSuccess)
-		e = cudaStreamSynchronize(st);
-	cudaFree(d3);
-	if (e != cudaSuccess)
-		return fail_cuda(e, "rsx_verify");
+	unsigned long long h3[3] = {0, 0, 0};
+	if (n) { // the three accumulators live in the (zeroed) head of the cached workspace
+		Plan P;
+		make_plan(P, 2, layout, kd, 0);
+		Lease L;
+		if ((r = acquire(L, dev, P.total)))
+			return r;
+		L.enqueued(st);
+		unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
+		WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
+		CU(zero_workspace(P, wsp, st));
+		CU(launch_verify(data, n, layout->record_bytes, kd, ws->hist, g_dev[dev].num_sms, st));
+		CU(cudaMemcpyAsync(h3, ws->hist, sizeof(h3), cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		L.drained();
+	}
 	if (descents_out) *descents_out = h3[0];
 	if (sum_out) *sum_out = h3[1];
 	if (xor_out) *xor_out = h3[2];

@@ -132,9 +132,9 @@ cudaError_t launch_extract_keys(const void *recs, size_t n, uint32_t record_byte
 cudaError_t launch_gather_records(const void *src, const void *rank, int idx_bytes, void *dst, size_t n, uint32_t record_bytes,
                                   int num_sms, cudaStream_t st);
 
-// key-range routing counts (d_counts: 16 zeroed entries)
+// key-range routing counts (h_split: HOST array of nsplit splitters; d_counts: 16 zeroed device entries)
 cudaError_t launch_split_counts(const void *data, size_t n, uint32_t record_bytes, const KeyDesc &kd,
-                                const unsigned long long *d_split, uint32_t nsplit, unsigned long long *d_counts,
+                                const unsigned long long *h_split, uint32_t nsplit, unsigned long long *d_counts,
                                 int num_sms, cudaStream_t st);
 
 // hardware probe for the ticket ranking (see rsx_scatter.cuh); *d_mismatch must be zeroed

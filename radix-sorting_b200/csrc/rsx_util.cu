@@ -92,16 +92,17 @@ __global__ void verify_kernel(const typename Rec<ES>::type *__restrict__ data, s
 
 // Key-range routing: counts[j] = number of records whose derived key falls in range j, where the
 // range index is the number of splitters <= key (splitters ascending).  One read of the records.
+// The splitters arrive as a kernel argument (constant bank: compares against uniform operands, no
+// shared-memory loads per key); unused entries are ~0 so that no key reaches them.
+struct SplitTable {
+	unsigned long long s[16];
+};
 template <int ES>
-__global__ void split_counts_kernel(const typename Rec<ES>::type *__restrict__ data, size_t n, KeyDesc kd,
-                                    const unsigned long long *__restrict__ split, uint32_t nsplit,
-                                    unsigned long long *counts) {
-	__shared__ unsigned long long s_split[16];
+__global__ void __launch_bounds__(512) split_counts_kernel(const typename Rec<ES>::type *__restrict__ data, size_t n, KeyDesc kd,
+                                                           SplitTable split, uint32_t nsplit, unsigned long long *counts) {
 	__shared__ unsigned int s_cnt[16];
-	if (threadIdx.x < 16) {
-		s_split[threadIdx.x] = threadIdx.x < nsplit ? split[threadIdx.x] : ~0ULL;
+	if (threadIdx.x < 16)
 		s_cnt[threadIdx.x] = 0;
-	}
 	__syncthreads();
 	uint32_t local[16];
 #pragma unroll
@@ -110,11 +111,14 @@ __global__ void split_counts_kernel(const typename Rec<ES>::type *__restrict__ d
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
 		const unsigned long long k = derive_key(key_word<ES>(data[i], kd.word_sel), kd);
 		uint32_t d = 0;
-		for (uint32_t j = 0; j < nsplit; ++j)
-			d += k >= s_split[j];
+#pragma unroll
+		for (int j = 0; j < 15; ++j)
+			if (j < (int)nsplit) // uniform
+				d += k >= split.s[j];
 #pragma unroll
 		for (int j = 0; j < 16; ++j)
-			local[j] += (d == (uint32_t)j);
+			if (j <= (int)nsplit) // uniform
+				local[j] += (d == (uint32_t)j);
 	}
 #pragma unroll
 	for (int j = 0; j < 16; ++j) {
@@ -239,15 +243,18 @@ inline int grid_for(size_t n, int threads, int cap) {
 } // namespace
 
 cudaError_t launch_split_counts(const void *data, size_t n, uint32_t record_bytes, const KeyDesc &kd,
-                                const unsigned long long *d_split, uint32_t nsplit, unsigned long long *d_counts,
+                                const unsigned long long *h_split, uint32_t nsplit, unsigned long long *d_counts,
                                 int num_sms, cudaStream_t st) {
 	const int g = grid_for(n, 512, num_sms * 4);
+	SplitTable t;
+	for (uint32_t j = 0; j < 16; ++j)
+		t.s[j] = j < nsplit ? h_split[j] : ~0ULL;
 	switch (record_bytes) {
-	case 1: split_counts_kernel<1><<<g, 512, 0, st>>>(static_cast<const uint8_t *>(data), n, kd, d_split, nsplit, d_counts); break;
-	case 2: split_counts_kernel<2><<<g, 512, 0, st>>>(static_cast<const uint16_t *>(data), n, kd, d_split, nsplit, d_counts); break;
-	case 4: split_counts_kernel<4><<<g, 512, 0, st>>>(static_cast<const uint32_t *>(data), n, kd, d_split, nsplit, d_counts); break;
-	case 8: split_counts_kernel<8><<<g, 512, 0, st>>>(static_cast<const unsigned long long *>(data), n, kd, d_split, nsplit, d_counts); break;
-	case 16: split_counts_kernel<16><<<g, 512, 0, st>>>(static_cast<const ulonglong2 *>(data), n, kd, d_split, nsplit, d_counts); break;
+	case 1: split_counts_kernel<1><<<g, 512, 0, st>>>(static_cast<const uint8_t *>(data), n, kd, t, nsplit, d_counts); break;
+	case 2: split_counts_kernel<2><<<g, 512, 0, st>>>(static_cast<const uint16_t *>(data), n, kd, t, nsplit, d_counts); break;
+	case 4: split_counts_kernel<4><<<g, 512, 0, st>>>(static_cast<const uint32_t *>(data), n, kd, t, nsplit, d_counts); break;
+	case 8: split_counts_kernel<8><<<g, 512, 0, st>>>(static_cast<const unsigned long long *>(data), n, kd, t, nsplit, d_counts); break;
+	case 16: split_counts_kernel<16><<<g, 512, 0, st>>>(static_cast<const ulonglong2 *>(data), n, kd, t, nsplit, d_counts); break;
 	default: return cudaErrorInvalidValue;
 	}
 	count_launch();
