@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 	constexpr int WARPS = SM::kWarps;
 	constexpr int LB = Cfg::kLookback;
 	constexpr uint32_t FULL = 0xFFFFFFFFu;
+	static_assert(THREADS >= kBins && THREADS % 32 == 0, "one digit thread per bin: the digit scan synchronises 256 threads");
 
 	extern __shared__ __align__(128) unsigned char smem[];
 	R *s_stage = reinterpret_cast<R *>(smem);

@@ -90,7 +90,7 @@ def test_workspace_sizing_and_options_need_no_device(rsx):
     w32 = L.rsx_workspace_bytes(n, C.byref(u32), 0)
     assert 0 < w32 - 4 * -(-n // 10240) * 256 * 4 <= head + 4096   # 4 columns x 10 240-record tiles, 4-byte status words
     w64 = L.rsx_workspace_bytes(n, C.byref(u64), 0)
-    assert 0 < w64 - 8 * -(-n // 8192) * 256 * 4 <= head + 4096    # 8 columns x 8 192-record tiles
+    assert 0 < w64 - 8 * -(-n // 9216) * 256 * 4 <= head + 4096    # 8 columns x 9 216-record tiles
     wide = L.rsx_workspace_bytes(1 << 30, C.byref(u32), 0)         # n >= 2^30: 8-byte status words
     assert wide > 2 * w32 - head
     # rank sort: two record buffers beside the indices, nothing extra for 4/8-byte index types
