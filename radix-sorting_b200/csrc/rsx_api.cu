@@ -130,10 +130,15 @@ int probe_rank_mode(int dev) {
 	return mode;
 }
 
+// The pinned slot of a lease: the mirrored pass table, then a read-back area for histograms (D2H
+// copies into pageable memory are staged by the driver and cost tens of microseconds more).
+constexpr size_t kPinnedReadback = 256, kPinnedBytes = kPinnedReadback + sizeof(unsigned long long) * kMaxCols * kBins;
+
 struct Lease {
 	int dev = -1;
 	void *ptr = nullptr;
 	Ctl *pinned = nullptr;
+	unsigned long long *readback() const { return reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(pinned) + kPinnedReadback); }
 	bool cached = false;
 	bool own_pinned = false;
 	// Set once kernels that use the leased memory have been enqueued; cleared by the final
@@ -225,7 +230,7 @@ int acquire(Lease &L, int dev, size_t bytes) {
 			D.ws_bytes = bytes;
 		}
 		if (!D.pinned)
-			CU(cudaHostAlloc((void **)&D.pinned, sizeof(Ctl), cudaHostAllocMapped));
+			CU(cudaHostAlloc((void **)&D.pinned, kPinnedBytes, cudaHostAllocMapped));
 		D.busy = true;
 		L.ptr = D.ws;
 		L.pinned = D.pinned;
@@ -234,7 +239,7 @@ int acquire(Lease &L, int dev, size_t bytes) {
 	}
 	lk.unlock(); // another host thread is sorting on this device: private scratch for this call
 	CU(cudaMalloc(&L.ptr, bytes));
-	CU(cudaHostAlloc((void **)&L.pinned, sizeof(Ctl), cudaHostAllocMapped));
+	CU(cudaHostAlloc((void **)&L.pinned, kPinnedBytes, cudaHostAllocMapped));
 	L.own_pinned = true;
 	return RSX_OK;
 }
@@ -1136,8 +1141,11 @@ int rsx_histogram(const void *src, size_t n, const rsx_layout *layout, uint64_t 
 		return r;
 	rep->live_mask = L.pinned->live_mask; // report the probe even when the input is presorted
 	rep->ncols = L.pinned->ncols;
-	if (hist_out)
-		CU(cudaMemcpy(hist_out, ws->hist, sizeof(uint64_t) * kBins * kd.key_bytes, cudaMemcpyDeviceToHost));
+	if (hist_out) {
+		CU(cudaMemcpyAsync(L.readback(), ws->hist, sizeof(uint64_t) * kBins * kd.key_bytes, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		memcpy(hist_out, L.readback(), sizeof(uint64_t) * kBins * kd.key_bytes);
+	}
 	if (descents_out)
 		CU(cudaMemcpy(descents_out, &ws->descents, sizeof(uint64_t), cudaMemcpyDeviceToHost));
 	return RSX_OK;
@@ -1182,9 +1190,10 @@ int rsx_histogram_column(const void *src, size_t n, const rsx_layout *layout, in
 	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
 	CU(zero_workspace(P, wsp, st));
 	CU(launch_histogram(src, n, layout->record_bytes, k1, ws, g_dev[dev].num_sms, st));
-	CU(cudaMemcpyAsync(hist_out, ws->hist, sizeof(uint64_t) * kBins, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(L.readback(), ws->hist, sizeof(uint64_t) * kBins, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	L.drained();
+	memcpy(hist_out, L.readback(), sizeof(uint64_t) * kBins);
 	return RSX_OK;
 }
 

@@ -88,6 +88,7 @@ class _Buffers:
     memory), a plain receive buffer for the all-to-all exchange, and -- when the caller's tensor has
     no slack -- a source copy with capacity."""
     symm = {}   # key -> (tensor, handle), or None once symmetric memory turned out to be unavailable
+    gather = {}  # (bytes, world, device) -> staging buffers of the all-gather callback
     plain = {}
     src = {}
     symm_error = None
@@ -151,11 +152,23 @@ def partitioned_sort(keys, kf, group=None, n: Optional[int] = None, ops=None, fu
 
     def cb_allgather(ctx, send, recv, nbytes):
         try:
-            mine = torch.from_numpy(np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), shape=(nbytes,)).copy())
-            mine = mine.to(coll_dev)
-            out = torch.empty(world * nbytes, dtype=torch.uint8, device=coll_dev)
-            dist.all_gather_into_tensor(out, mine, group=group)
-            np.ctypeslib.as_array(C.cast(recv, C.POINTER(C.c_uint8)), shape=(world * nbytes,))[:] = out.cpu().numpy()
+            key = (nbytes, world, dev.index if on_gpu else -1)
+            bufs = _Buffers.gather.get(key)
+            if bufs is None:  # pinned staging + device tensors, reused by every later call
+                pin_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=on_gpu)
+                pin_out = torch.empty(world * nbytes, dtype=torch.uint8, pin_memory=on_gpu)
+                dev_in = torch.empty(nbytes, dtype=torch.uint8, device=coll_dev) if on_gpu else pin_in
+                dev_out = torch.empty(world * nbytes, dtype=torch.uint8, device=coll_dev) if on_gpu else pin_out
+                bufs = _Buffers.gather[key] = (pin_in, pin_out, dev_in, dev_out)
+            pin_in, pin_out, dev_in, dev_out = bufs
+            C.memmove(pin_in.data_ptr(), send, nbytes)
+            if on_gpu:
+                dev_in.copy_(pin_in, non_blocking=True)
+            dist.all_gather_into_tensor(dev_out, dev_in, group=group)
+            if on_gpu:
+                pin_out.copy_(dev_out, non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+            C.memmove(recv, pin_out.data_ptr(), world * nbytes)
             return 0
         except Exception as e:  # noqa: BLE001
             state["err"] = e
