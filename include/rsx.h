@@ -128,6 +128,22 @@ int rsx_scatter_pass(const void *src, void *dst, const void *payload_src, void *
 int rsx_scatter_pass_to(const void *src, size_t n, const rsx_layout *layout, int col,
                         const uint8_t *owner, const uint64_t *dest_base, int ndest, void *stream);
 
+/* Append-mode form of the two fused passes, for keys-only records (record_bytes == key_bytes): a
+ * tile's run for destination D is placed where D's append cursor says -- one system-scope atomicAdd
+ * on *dest_cursor[D] (a uint64 record count in D's memory, zeroed by its owner) -- instead of at an
+ * offset derived from exact per-source counts, so no histogram pass has to precede it and the pass
+ * needs no look-back.  The order in which runs land is arbitrary, which is invisible for keys-only
+ * records.  col >= 0: destination = owner[digit]; col < 0: key ranges (splitters).  A run that would
+ * exceed dest_capacity[D] records is dropped and *overflow_out set (src is only read: retry with
+ * more room).  rsx_histogram_column_sampled counts one column over every stride-th record: the
+ * estimate the bucket ranges are balanced with. */
+int rsx_scatter_pass_append(const void *src, size_t n, const rsx_layout *layout, int col, const uint8_t *owner,
+                            const uint64_t *splitters, int nsplit, const uint64_t *dest_base,
+                            const uint64_t *dest_cursor, const uint64_t *dest_capacity, int ndest,
+                            uint32_t *overflow_out, void *stream);
+int rsx_histogram_column_sampled(const void *src, size_t n, const rsx_layout *layout, int col, size_t stride,
+                                 uint64_t *hist_out /* 256 */, void *stream);
+
 /* Key-range routing for skewed multi-GPU inputs (sample-sort style): `splitters` are nsplit
  * (<= 15) ascending DERIVED keys; a record's destination is the number of splitters <= its
  * derived key (0 .. nsplit).  rsx_split_counts counts the records per destination (HOST array of
@@ -202,6 +218,8 @@ typedef struct rsx_multi_report {
 	uint32_t key_range;       /* 1: routed by sample-based key ranges    */
 	uint32_t live_mask;
 	uint32_t fused;           /* 1: records went straight into peer memory */
+	uint32_t append;          /* 1: keys-only append-mode exchange (sampled routing, no histogram pass) */
+	uint32_t pad;
 	uint64_t n_total;
 	uint64_t needed_capacity; /* records each buffer must hold (valid also on RSX_ERR_WORKSPACE) */
 	double imbalance;
@@ -211,6 +229,7 @@ typedef struct rsx_multi_report {
 #define RSX_MULTI_NO_FUSED 1u     /* exchange through comm->alltoallv instead of peer stores */
 #define RSX_MULTI_NO_KEY_RANGE 2u /* always route by bucket ranges (tests)                  */
 #define RSX_MULTI_FULL_HISTOGRAM 4u /* count every column for routing, not just the top one (tests) */
+#define RSX_MULTI_EXACT 8u        /* keys-only records too take the exact (histogram + offsets) exchange */
 
 int rsx_multi_route(const uint64_t *hist_all /* [world][cols][256] */, int world, int cols, int rank,
                     double skew_threshold, rsx_route *out);

@@ -36,7 +36,7 @@ RSX_ERR_WORKSPACE, RSX_ERR_IDX_RANGE, RSX_ERR_MIXED_MEMORY = -4, -5, -6
 #: every symbol include/rsx.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "rsx_sort", "rsx_sort_rank", "rsx_histogram", "rsx_histogram_column", "rsx_scatter_pass", "rsx_scatter_pass_to",
-    "rsx_split_counts", "rsx_split_pass_to",
+    "rsx_split_counts", "rsx_split_pass_to", "rsx_scatter_pass_append", "rsx_histogram_column_sampled",
     "rsx_multi_route", "rsx_multi_splitters", "rsx_sort_shard", "rsx_sort_multi",
     "rsx_workspace_bytes",
     "rsx_reserve", "rsx_release", "rsx_fill_keys", "rsx_verify", "rsx_strerror",
@@ -59,7 +59,7 @@ class RsxReport(C.Structure):
 
 
 RSX_MAX_RANKS = 16
-MULTI_NO_FUSED, MULTI_NO_KEY_RANGE, MULTI_FULL_HISTOGRAM = 1, 2, 4
+MULTI_NO_FUSED, MULTI_NO_KEY_RANGE, MULTI_FULL_HISTOGRAM, MULTI_EXACT = 1, 2, 4, 8
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
 BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
@@ -101,7 +101,7 @@ class RsxRoute(C.Structure):
 class RsxMultiReport(C.Structure):
     """struct rsx_multi_report."""
     _fields_ = [("routing_column", C.c_int32), ("key_range", C.c_uint32), ("live_mask", C.c_uint32), ("fused", C.c_uint32),
-                ("n_total", C.c_uint64), ("needed_capacity", C.c_uint64), ("imbalance", C.c_double),
+                ("append", C.c_uint32), ("pad", C.c_uint32), ("n_total", C.c_uint64), ("needed_capacity", C.c_uint64), ("imbalance", C.c_double),
                 ("seconds_histogram", C.c_double), ("seconds_routing", C.c_double), ("seconds_exchange", C.c_double),
                 ("seconds_local_sort", C.c_double)]
 

@@ -501,7 +501,9 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
                            const KeyDesc &kd, int col, const WsHead *ws, bool forced, void *status,
                            unsigned int *ticket, bool wide, int num_sms, cudaStream_t st,
                            const unsigned long long *dest_base, const unsigned char *owner,
-                           const unsigned long long *splitters, int nsplit, int ndest) {
+                           const unsigned long long *splitters, int nsplit, int ndest,
+                           const unsigned long long *dest_cursor, const unsigned long long *dest_capacity,
+                           unsigned int *overflow) {
 	ScatterParams sp;
 	sp.pb = pb;
 	sp.n = n;
@@ -520,6 +522,9 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
 	sp.dest_base = dest_base;
 	sp.owner = owner;
 	sp.ndest = (uint32_t)ndest;
+	sp.dest_cursor = dest_cursor;
+	sp.dest_capacity = dest_capacity;
+	sp.overflow = overflow;
 	// keys-only records: the order inside a (tile, destination) run is free -> TMA bulk stores
 	sp.unordered_runs = (dest_base != nullptr && record_bytes == kd.key_bytes && record_bytes < 16 && g_fused_bulk.load(std::memory_order_relaxed)) ? 1u : 0u;
 	sp.kd = kd;
@@ -1359,6 +1364,100 @@ int rsx_split_pass_to(const void *src, size_t n, const rsx_layout *layout, const
 	                  ws->dest_base, ws->owner, reinterpret_cast<const unsigned long long *>(splitters), nsplit, nsplit + 1));
 	CU(cudaStreamSynchronize(st));
 	L.drained();
+	return RSX_OK;
+}
+
+// Append-mode partition + exchange (keys-only records): like rsx_scatter_pass_to / rsx_split_pass_to,
+// but a tile's run is placed where the destination's append cursor says instead of at an offset
+// derived from exact per-source counts -- no routing histogram has to precede the pass.
+int rsx_scatter_pass_append(const void *src, size_t n, const rsx_layout *layout, int col, const uint8_t *owner,
+                            const uint64_t *splitters, int nsplit, const uint64_t *dest_base,
+                            const uint64_t *dest_cursor, const uint64_t *dest_capacity, int ndest,
+                            uint32_t *overflow_out, void *stream) {
+	KeyDesc kd;
+	int r = check_layout(layout, &kd);
+	if (r)
+		return r;
+	if (!src || !dest_base || !dest_cursor || !dest_capacity || !overflow_out || n < 1 || ndest < 1 || ndest > kMaxSplit + 1)
+		return RSX_ERR_INVALID;
+	if (layout->record_bytes != kd.key_bytes)
+		return RSX_ERR_INVALID; // append order is arbitrary: only where equal records are indistinguishable
+	unsigned char own[kBins];
+	if (col >= 0) {
+		if (!owner || col >= (int)kd.key_bytes)
+			return RSX_ERR_INVALID;
+		for (int b = 0; b < kBins; ++b) {
+			if (owner[b] >= ndest || (b && owner[b] < owner[b - 1]))
+				return RSX_ERR_INVALID;
+			own[b] = owner[b];
+		}
+		nsplit = 0;
+	} else {
+		if ((r = check_splitters(splitters, nsplit)) || ndest != nsplit + 1)
+			return r ? r : RSX_ERR_INVALID;
+		for (int b = 0; b < kBins; ++b)
+			own[b] = (unsigned char)(b <= nsplit ? b : nsplit); // "digit" == destination
+	}
+	int dev;
+	if ((r = current_device(&dev)))
+		return r;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	Plan P;
+	make_plan(P, n, layout, kd, 0, 0);
+	Lease L;
+	if ((r = acquire(L, dev, P.total)))
+		return r;
+	L.enqueued(st);
+	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
+	const int sms = g_dev[dev].num_sms;
+	CU(cudaMemsetAsync(wsp + P.off_head, 0, kWsZeroBytes, st)); // ticket + overflow flag; no look-back state in this mode
+	CU(cudaMemcpyAsync(ws->dest_base, dest_base, sizeof(uint64_t) * ndest, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ws->dest_cursor, dest_cursor, sizeof(uint64_t) * ndest, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ws->dest_capacity, dest_capacity, sizeof(uint64_t) * ndest, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(ws->owner, own, kBins, cudaMemcpyHostToDevice, st));
+	PassBuffers pb{};
+	pb.rec_first = src;
+	const int c = col >= 0 ? col : 0;
+	CU(launch_scatter(pb, P.n, P.rb, 0, P.kd, c, ws, true, wsp + (size_t)c * P.status_bytes, &ws->tickets[c], P.wide, sms, st,
+	                  ws->dest_base, ws->owner, col >= 0 ? nullptr : reinterpret_cast<const unsigned long long *>(splitters),
+	                  nsplit, ndest, ws->dest_cursor, ws->dest_capacity, &ws->overflow));
+	CU(cudaMemcpyAsync(L.readback(), &ws->overflow, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	L.drained();
+	*overflow_out = *reinterpret_cast<unsigned int *>(L.readback());
+	return RSX_OK;
+}
+
+// The 256-bin histogram of one column over a SAMPLE of the records (every stride-th one): what
+// the append-mode exchange balances its bucket ranges with.
+int rsx_histogram_column_sampled(const void *src, size_t n, const rsx_layout *layout, int col, size_t stride,
+                                 uint64_t *hist_out, void *stream) {
+	KeyDesc kd;
+	int r = check_layout(layout, &kd);
+	if (r)
+		return r;
+	if (!src || !hist_out || n < 1 || stride < 1 || col < 0 || col >= (int)kd.key_bytes)
+		return RSX_ERR_INVALID;
+	int dev;
+	if ((r = current_device(&dev)))
+		return r;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	Plan P;
+	rsx_layout l1 = *layout;
+	make_plan(P, 2, &l1, kd, 0);
+	Lease L;
+	if ((r = acquire(L, dev, P.total)))
+		return r;
+	L.enqueued(st);
+	unsigned char *wsp = static_cast<unsigned char *>(L.ptr);
+	WsHead *ws = reinterpret_cast<WsHead *>(wsp + P.off_head);
+	CU(zero_workspace(P, wsp, st));
+	CU(launch_sample_column_hist(src, n, layout->record_bytes, kd, col, stride, ws->hist, g_dev[dev].num_sms, st));
+	CU(cudaMemcpyAsync(L.readback(), ws->hist, sizeof(uint64_t) * kBins, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	L.drained();
+	memcpy(hist_out, L.readback(), sizeof(uint64_t) * kBins);
 	return RSX_OK;
 }
 

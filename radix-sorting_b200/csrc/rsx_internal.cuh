@@ -59,12 +59,15 @@ struct WsHead {
 	unsigned long long descents;               // #i: kdf(a[i]) > kdf(a[i+1])       (zeroed)
 	unsigned int tickets[kMaxCols];            // tile tickets, one per column      (zeroed)
 	unsigned long long key_or, key_nand;       // see Ctl                            (zeroed)
-	unsigned int pad0[2];
+	unsigned int overflow;                     // append-mode exchange: a run did not fit (zeroed)
+	unsigned int pad0[1];
 	// -- not zeroed below --
 	unsigned long long offs[kMaxCols * kBins]; // exclusive scan per column (radix_sort.hpp:72-80)
 	Ctl ctl;
 	unsigned long long dest_base[kBins];       // fused partition + exchange: per-destination base address
 	unsigned char owner[kBins];                // ... and the destination of every bucket
+	unsigned long long dest_cursor[kBins];     // append mode: address of every destination's cursor ...
+	unsigned long long dest_capacity[kBins];   // ... and the records it can take
 };
 constexpr size_t kWsZeroBytes = offsetof(WsHead, offs);
 
@@ -111,7 +114,8 @@ cudaError_t launch_scatter(const PassBuffers &pb, size_t n, uint32_t record_byte
                            bool forced, void *status, unsigned int *ticket, bool wide_offsets,
                            int num_sms, cudaStream_t st, const unsigned long long *dest_base = nullptr,
                            const unsigned char *owner = nullptr, const unsigned long long *splitters = nullptr,
-                           int nsplit = 0, int ndest = 0);
+                           int nsplit = 0, int ndest = 0, const unsigned long long *dest_cursor = nullptr,
+                           const unsigned long long *dest_capacity = nullptr, unsigned int *overflow = nullptr);
 
 PassGeometry scatter_geometry(uint32_t record_bytes, int payload_bytes);
 
@@ -125,6 +129,9 @@ cudaError_t launch_iota_if_early(void *index_buffer, int idx_bytes, size_t n, co
                                  cudaStream_t st);
 cudaError_t launch_narrow_index(const uint32_t *wide0, const uint32_t *wide1, void *index_buffer,
                                 int idx_bytes, size_t n, const Ctl *ctl, cudaStream_t st);
+
+cudaError_t launch_sample_column_hist(const void *data, size_t n, uint32_t record_bytes, const KeyDesc &kd, int col, size_t stride,
+                                      unsigned long long *d_hist, int num_sms, cudaStream_t st);
 
 // records of any size: key extraction + final gather around a rank sort of the keys
 cudaError_t launch_extract_keys(const void *recs, size_t n, uint32_t record_bytes, uint32_t key_offset, uint32_t key_bytes,

@@ -225,6 +225,129 @@ int rsx_sort_shard(const rsx_comm *comm, const rsx_shard_ops *ops_in, void *src,
 	int r;
 	auto t0 = clk::now();
 
+	// Keys-only records over peer-mapped buffers: append-mode exchange.  Equal records are
+	// indistinguishable, so neither the order in which the sources' runs land in a receive buffer
+	// nor exact per-source offsets matter: bucket ranges (or key ranges) are balanced on a SAMPLE of
+	// the routing digit, every (tile, destination) run reserves its place with one atomic on the
+	// destination's append cursor, and the full routing histogram pass (and, for skewed keys, the
+	// counting pass) disappears.  Anything else takes the exact path below.
+	if (!ops_in && recv_peers && !(flags & (RSX_MULTI_NO_FUSED | RSX_MULTI_EXACT)) && L->record_bytes == L->key_bytes &&
+	    cols > 1 && world > 1 && capacity * rb >= 64) {
+		const uint64_t coff = ((capacity * rb) & ~(uint64_t)15) - 16; // the cursor: last aligned 16 bytes of the receive buffer
+		const uint64_t cap_eff = coff / rb;
+		const size_t stride = std::max<size_t>(1, n / 131072);
+		std::vector<uint64_t> h(256 + 2), g((256 + 2) * (size_t)world);
+		if (n && (r = rsx_histogram_column_sampled(src, n, L, cols - 1, stride, h.data(), stream)))
+			return r;
+		h[256] = n;
+		h[257] = cap_eff;
+		if ((r = comm->allgather(comm->ctx, h.data(), g.data(), h.size() * sizeof(uint64_t))))
+			return r;
+		const size_t hw = (size_t)cols * 256;
+		std::vector<uint64_t> hall(hw * world, 0);
+		uint64_t n_total = 0, n_max = 0, cap_min = ~0ULL, tot = 0, mx = 0, colsum[256] = {};
+		for (int q = 0; q < world; ++q) {
+			const uint64_t *hq = &g[(size_t)q * 258];
+			uint64_t sq = 0;
+			for (int b = 0; b < 256; ++b) {
+				hall[(size_t)q * hw + (size_t)(cols - 1) * 256 + b] = hq[b];
+				colsum[b] += hq[b];
+				sq += hq[b];
+			}
+			for (int c = 0; c + 1 < cols; ++c) // unknown columns: "not constant"
+				hall[(size_t)q * hw + (size_t)c * 256] = sq - sq / 2, hall[(size_t)q * hw + (size_t)c * 256 + 1] = sq / 2;
+			n_total += hq[256];
+			n_max = std::max(n_max, hq[256]);
+			cap_min = std::min(cap_min, hq[257]);
+		}
+		for (int b = 0; b < 256; ++b) {
+			tot += colsum[b];
+			mx = std::max(mx, colsum[b]);
+		}
+		if (tot && mx != tot) { // the sampled routing digit is live (else: constant high bytes, exact path)
+			rsx_route route;
+			if ((r = rsx_multi_route(hall.data(), world, cols, rank, (flags & RSX_MULTI_NO_KEY_RANGE) ? 1e30 : 1.15, &route)))
+				return r;
+			rep->live_mask = 1u << (cols - 1);
+			rep->n_total = n_total;
+			rep->seconds_histogram = since(t0);
+			t0 = clk::now();
+			uint64_t splitters[RSX_MAX_RANKS] = {};
+			int nsplit = 0;
+			if (route.key_range && world - 1 <= 15) {
+				constexpr size_t kSamples = 8192;
+				std::vector<uint64_t> mine(1 + kSamples, ~0ULL), all((1 + kSamples) * world);
+				const size_t cnt = std::min(kSamples, n);
+				mine[0] = cnt;
+				if (cnt && (r = ops.sample(octx, src, n, L, cnt, mine.data() + 1, stream)))
+					return r;
+				if ((r = comm->allgather(comm->ctx, mine.data(), all.data(), mine.size() * sizeof(uint64_t))))
+					return r;
+				std::vector<uint64_t> pooled;
+				for (int q = 0; q < world; ++q) {
+					const uint64_t *pq = &all[(size_t)q * (1 + kSamples)];
+					pooled.insert(pooled.end(), pq + 1, pq + 1 + pq[0]);
+				}
+				nsplit = world - 1;
+				rsx_multi_splitters(pooled.data(), pooled.size(), world, splitters);
+				rep->key_range = 1;
+			} else {
+				rep->routing_column = route.routing_column;
+			}
+			// room for the estimated shard + sampling error; every rank reaches the same verdict
+			const double est = route.key_range ? (double)n_total / world : (double)route.max_n_out / (double)std::max<uint64_t>(tot, 1) * (double)n_total;
+			rep->needed_capacity = (uint64_t)(std::max(est * 1.03, (double)n_max)) + 4096;
+			if (rep->needed_capacity > cap_min)
+				return RSX_ERR_WORKSPACE;
+			rep->seconds_routing = since(t0);
+			t0 = clk::now();
+			uint64_t base[RSX_MAX_RANKS], cursor[RSX_MAX_RANKS], caps[RSX_MAX_RANKS];
+			for (int d = 0; d < world; ++d) {
+				base[d] = (uint64_t)(uintptr_t)recv_peers[d];
+				cursor[d] = base[d] + coff;
+				caps[d] = cap_eff;
+			}
+			if (cudaMemsetAsync(static_cast<unsigned char *>(recv) + coff, 0, 16, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+				return RSX_ERR_CUDA;
+			if ((r = comm->barrier(comm->ctx))) // every cursor is zero, nobody still sorts out of its receive buffer
+				return r;
+			uint32_t overflow = 0;
+			if (n && (r = rsx_scatter_pass_append(src, n, L, rep->key_range ? -1 : route.routing_column, route.owner, splitters,
+			                                      nsplit, base, cursor, caps, world, &overflow, stream)))
+				return r;
+			if ((r = comm->barrier(comm->ctx))) // all runs have landed
+				return r;
+			uint64_t got = 0;
+			if (cudaMemcpy(&got, static_cast<unsigned char *>(recv) + coff, sizeof(got), cudaMemcpyDeviceToHost) != cudaSuccess)
+				return RSX_ERR_CUDA;
+			uint64_t mine2[2] = {overflow, got}, all2[2 * RSX_MAX_RANKS];
+			if ((r = comm->allgather(comm->ctx, mine2, all2, sizeof(mine2))))
+				return r;
+			uint64_t any_overflow = 0, got_max = 0, got_sum = 0;
+			for (int q = 0; q < world; ++q) {
+				any_overflow |= all2[2 * q];
+				got_max = std::max(got_max, all2[2 * q + 1]);
+				got_sum += all2[2 * q + 1];
+			}
+			if (any_overflow || got_sum != n_total) { // a run did not fit (src is intact): ask for more room
+				rep->needed_capacity = (uint64_t)((double)std::max(got_max, rep->needed_capacity) * 1.25) + 4096;
+				return RSX_ERR_WORKSPACE;
+			}
+			rep->fused = 1;
+			rep->append = 1;
+			rep->imbalance = (double)got_max / std::max(1.0, (double)n_total / world);
+			rep->seconds_exchange = since(t0);
+			t0 = clk::now();
+			*n_out = (size_t)got;
+			*result = recv;
+			if (got > 1 && (r = ops.sort(octx, recv, src, (size_t)got, L, result, stream)))
+				return r;
+			rep->seconds_local_sort = since(t0);
+			return RSX_OK;
+		}
+		t0 = clk::now();
+	}
+
 	// 1-2. histograms of every rank, visible to every rank.  Routing only needs the TOP column, and
 	// counting one column runs at HBM speed (one atomic per record instead of key_bytes), so that
 	// is tried first; only when the top column is constant over all ranks (keys with constant high

@@ -67,6 +67,14 @@ struct ScatterParams {
 	// order INSIDE one (tile, destination) run is free -- its 16-byte-aligned body can then leave as
 	// ONE TMA bulk store (shared -> peer memory) instead of LSU stores.
 	uint32_t unordered_runs;
+	// Append mode (keys-only multi-GPU exchange without a routing histogram): every destination has
+	// an append cursor in ITS memory; a tile reserves room for its run with one system-scope atomic
+	// and needs neither the exact per-source offsets nor a look-back.  dest_cursor[k] = address of
+	// destination k's cursor (records), dest_capacity[k] = records it can take; a run that would not
+	// fit is dropped and *overflow set (the caller retries with more room; src is only read).
+	const unsigned long long *dest_cursor;
+	const unsigned long long *dest_capacity;
+	unsigned int *overflow;
 	// Key-range routing (DIGIT_SPLIT): the "digit" of a record is the number of splitters that are
 	// <= its derived key, i.e. its destination among nsplit + 1 key ranges.
 	KeyDesc kd;
@@ -479,6 +487,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		// ---- 3a. digit threads: warp prefixes, tile scan, publish aggregate ----
 		constexpr bool fusedm = FUSED;
 		uint32_t tcount = 0, tstart = 0;
+		[[maybe_unused]] unsigned long long append_off = 0;
 		if (tid < kBins) {
 			uint32_t c[WARPS];
 			if constexpr (FUSED) {
@@ -496,7 +505,11 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 			// tail padding sorts last (after every real record of the last used digit): not part of the aggregate
 			const uint32_t pad_digit = DM == DIGIT_SPLIT ? p.nsplit : (uint32_t)kBins - 1;
 			const uint32_t agg = (!full && tid == pad_digit) ? tcount - ((uint32_t)TILE - valid) : tcount;
-			st_status(&status[(size_t)tile * kBins + tid], (OffT)((tile == 0 ? SB::kPfx : SB::kAgg) | (OffT)agg));
+			bool append = false;
+			if constexpr (FUSED)
+				append = p.dest_cursor != nullptr;
+			if (!append)
+				st_status(&status[(size_t)tile * kBins + tid], (OffT)((tile == 0 ? SB::kPfx : SB::kAgg) | (OffT)agg));
 			// exclusive scan of tcount over the 256 digit threads (8 warps)
 			uint32_t x = tcount;
 #pragma unroll
@@ -527,6 +540,34 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 				run += c[w];
 			}
 			tcount = agg;
+			if constexpr (FUSED) {
+				if (append) {
+					// records per destination (a contiguous digit range, hence contiguous lanes), then
+					// one system-scope atomic per destination reserves the run's place in the owner's
+					// buffer; the reply travels while the tile is being placed
+					const uint32_t D = my_owner;
+					const uint32_t grp = __match_any_sync(FULL, D);
+					uint32_t cnt = tcount;
+#pragma unroll
+					for (int o = 1; o < 32; o <<= 1) {
+						const uint32_t cnt2 = __shfl_down_sync(FULL, cnt, o);
+						if (lane + o < 32 && ((grp >> (lane + o)) & 1u))
+							cnt += cnt2;
+					}
+					if (lane == (uint32_t)__ffs(grp) - 1)
+						atomicAdd(&s_dcount[D], cnt);
+					if (tid == 0 || p.owner[tid - 1] != D)
+						s_dstart[D] = tstart;
+					asm volatile("bar.sync 1, 256;" ::: "memory");
+					if (tid < p.ndest) {
+						const uint32_t mine = s_dcount[tid];
+						unsigned long long off = 0;
+						if (mine)
+							off = atomicAdd_system(reinterpret_cast<unsigned long long *>(p.dest_cursor[tid]), (unsigned long long)mine);
+						append_off = off;
+					}
+				}
+			}
 		}
 		RSX_T(3);
 
@@ -579,7 +620,21 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		// ---- 3b. decoupled look-back, one chain per digit.  The first round is split over two
 		//      threads per digit (warp w and warp w+8), so 2*LB predecessors cost one L2 round trip;
 		//      whatever is still unresolved afterwards is walked serially by the digit thread. ----
-		{
+		bool append_mode = false;
+		if constexpr (FUSED)
+			append_mode = p.dest_cursor != nullptr;
+		if (append_mode) {
+			// append mode: no look-back at all -- the reservation made after the digit scan is the
+			// run's offset in the destination
+			if (tid < p.ndest) {
+				const uint32_t mine = s_dcount[tid];
+				if (mine && append_off + mine > p.dest_capacity[tid]) {
+					*p.overflow = 1u; // does not fit: drop the run, the caller retries with more room
+					s_dcount[tid] = 0;
+				}
+				s_dexcl[tid] = append_off;
+			}
+		} else {
 			OffT part = 0;
 			uint32_t st = 0, used = 0; // st: 0 = only aggregates so far, 1 = reached a prefix, 2 = hit an unpublished word
 			if (half < (kPair ? 2u : 1u)) {

@@ -234,6 +234,25 @@ __global__ void gather_records_kernel(const W *__restrict__ src, const I *__rest
 	}
 }
 
+// Digit histogram of column `col` over every stride-th record (append-mode routing estimate).
+template <int ES>
+__global__ void sample_column_hist_kernel(const typename Rec<ES>::type *__restrict__ data, size_t n, KeyDesc kd, uint32_t col,
+                                          size_t stride, unsigned long long *hist) {
+	__shared__ unsigned int s_h[kBins];
+	for (int b = threadIdx.x; b < kBins; b += blockDim.x)
+		s_h[b] = 0;
+	__syncthreads();
+	const size_t m = (n + stride - 1) / stride;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x) {
+		const unsigned long long k = derive_key(key_word<ES>(data[i * stride], kd.word_sel), kd);
+		atomicAdd(&s_h[(uint32_t)(k >> (8u * col)) & 0xFFu], 1u);
+	}
+	__syncthreads();
+	for (int b = threadIdx.x; b < kBins; b += blockDim.x)
+		if (s_h[b])
+			atomicAdd(&hist[b], (unsigned long long)s_h[b]);
+}
+
 inline int grid_for(size_t n, int threads, int cap) {
 	size_t g = (n + threads - 1) / threads;
 	if (g < 1) g = 1;
@@ -339,6 +358,21 @@ cudaError_t launch_extract_keys(const void *recs, size_t n, uint32_t record_byte
 	case 2: extract_keys_kernel<<<g, 256, 0, st>>>(r, n, record_bytes, key_offset, static_cast<uint16_t *>(keys_out)); break;
 	case 4: extract_keys_kernel<<<g, 256, 0, st>>>(r, n, record_bytes, key_offset, static_cast<uint32_t *>(keys_out)); break;
 	case 8: extract_keys_kernel<<<g, 256, 0, st>>>(r, n, record_bytes, key_offset, static_cast<unsigned long long *>(keys_out)); break;
+	default: return cudaErrorInvalidValue;
+	}
+	count_launch();
+	return cudaGetLastError();
+}
+
+cudaError_t launch_sample_column_hist(const void *data, size_t n, uint32_t record_bytes, const KeyDesc &kd, int col, size_t stride,
+                                      unsigned long long *d_hist, int num_sms, cudaStream_t st) {
+	const int g = grid_for((n + stride - 1) / stride, 256, num_sms * 8);
+	switch (record_bytes) {
+	case 1: sample_column_hist_kernel<1><<<g, 256, 0, st>>>(static_cast<const uint8_t *>(data), n, kd, (uint32_t)col, stride, d_hist); break;
+	case 2: sample_column_hist_kernel<2><<<g, 256, 0, st>>>(static_cast<const uint16_t *>(data), n, kd, (uint32_t)col, stride, d_hist); break;
+	case 4: sample_column_hist_kernel<4><<<g, 256, 0, st>>>(static_cast<const uint32_t *>(data), n, kd, (uint32_t)col, stride, d_hist); break;
+	case 8: sample_column_hist_kernel<8><<<g, 256, 0, st>>>(static_cast<const unsigned long long *>(data), n, kd, (uint32_t)col, stride, d_hist); break;
+	case 16: sample_column_hist_kernel<16><<<g, 256, 0, st>>>(static_cast<const ulonglong2 *>(data), n, kd, (uint32_t)col, stride, d_hist); break;
 	default: return cudaErrorInvalidValue;
 	}
 	count_launch();

@@ -81,6 +81,7 @@ class PartitionInfo:
     imbalance: float
     fused: bool
     seconds: dict = field(default_factory=dict)
+    append: bool = False
 
 
 class _Buffers:
@@ -122,7 +123,7 @@ def _symmetric_recv(capacity_elems, like, group):
 
 
 def partitioned_sort(keys, kf, group=None, n: Optional[int] = None, ops=None, fused: bool = True,
-                     key_range: bool = True):
+                     key_range: bool = True, exact: bool = False):
     """Globally sorts the concatenation (in rank order) of every rank's first `n` records of `keys`
     (default: all of it).  Returns (this rank's slice of the sorted sequence, PartitionInfo).
     `keys` is clobbered; tensor capacity beyond `n` is used as working space (a tensor without
@@ -200,7 +201,7 @@ def partitioned_sort(keys, kf, group=None, n: Optional[int] = None, ops=None, fu
 
     comm = rsx.RsxComm(rank, world, rsx.ALLGATHER_FN(cb_allgather), rsx.BARRIER_FN(cb_barrier),
                        rsx.ALLTOALLV_FN(cb_alltoallv), None)
-    flags = (0 if key_range else rsx.MULTI_NO_KEY_RANGE)
+    flags = (0 if key_range else rsx.MULTI_NO_KEY_RANGE) | (rsx.MULTI_EXACT if exact else 0)
 
     capacity = count  # records the caller's tensor can hold
     src = keys
@@ -252,8 +253,10 @@ def partitioned_sort(keys, kf, group=None, n: Optional[int] = None, ops=None, fu
     sec = {"histogram+allgather": rep.seconds_histogram, "routing": rep.seconds_routing,
            "partition+exchange": rep.seconds_exchange, "local_sort": rep.seconds_local_sort,
            "exchange": ("fused peer stores (NVLink)" if rep.fused else "all_to_all_single") +
+                       (", append mode (sampled routing, no histogram pass)" if rep.append else "") +
                        (", key-range routing" if rep.key_range else "")}
-    return res, PartitionInfo(routing, int(n_out.value), int(rep.n_total), float(rep.imbalance), bool(rep.fused), sec)
+    return res, PartitionInfo(routing, int(n_out.value), int(rep.n_total), float(rep.imbalance), bool(rep.fused), sec,
+                              bool(rep.append))
 
 
 # -------------------------------------------------------------------------------------------------

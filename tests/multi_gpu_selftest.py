@@ -55,10 +55,12 @@ def selftest(rsx, rank, world, dev, n_per=1 << 21):
             else:
                 data = keys.view(t.dtype)
             want, _, _ = pyoracle.Oracle().radix_sort(data, t.layout())
-        for fused in (True, False):
+        # keys-only records take the append-mode exchange by default; every case also runs the exact
+        # fused exchange and the NCCL all-to-all
+        for fused, exact in ((True, False), (True, True), (False, False)):
             work = torch.empty(int(shard.numel() * 1.3) + 4096, dtype=shard.dtype, device=dev)
             work[: shard.numel()].copy_(shard)
-            res, info = partitioned_sort(work, kf, n=n_per, fused=fused)
+            res, info = partitioned_sort(work, kf, n=n_per, fused=fused, exact=exact)
             mine = res.cpu().numpy().tobytes()
             parts = [None] * world if rank == 0 else None
             dist.gather_object(mine, parts, dst=0)
@@ -67,11 +69,12 @@ def selftest(rsx, rank, world, dev, n_per=1 << 21):
                 ok = b"".join(parts) == want.tobytes()
             flag = torch.tensor([1 if ok else 0], device=dev)
             dist.broadcast(flag, src=0)
-            results.append({"type": tname, "dist": dname, "fused": bool(info.fused), "requested_fused": fused,
+            results.append({"type": tname, "dist": dname, "fused": bool(info.fused), "append": bool(info.append),
+                            "requested": "fused" + ("-exact" if exact else "") if fused else "nccl",
                             "routing_column": info.routing_column, "imbalance": round(info.imbalance, 3),
                             "bit_exact_vs_oracle": bool(flag.item())})
             if not int(flag.item()):
-                raise AssertionError(f"multi-GPU selftest: {tname}/{dname} fused={fused} differs from the oracle")
+                raise AssertionError(f"multi-GPU selftest: {tname}/{dname} fused={fused} exact={exact} differs from the oracle")
             del work, res
         del shard, k
         torch.cuda.empty_cache()
