@@ -264,17 +264,22 @@ int rsx_sort_shard(const rsx_comm *comm, const rsx_shard_ops *ops_in, void *src,
 			tot += colsum[b];
 			mx = std::max(mx, colsum[b]);
 		}
-		if (tot && mx != tot) { // the sampled routing digit is live (else: constant high bytes, exact path)
-			rsx_route route;
-			if ((r = rsx_multi_route(hall.data(), world, cols, rank, (flags & RSX_MULTI_NO_KEY_RANGE) ? 1e30 : 1.15, &route)))
-				return r;
-			rep->live_mask = 1u << (cols - 1);
-			rep->n_total = n_total;
-			rep->seconds_histogram = since(t0);
-			t0 = clk::now();
-			uint64_t splitters[RSX_MAX_RANKS] = {};
-			int nsplit = 0;
-			if (route.key_range && world - 1 <= 15) {
+		// Routing by the TOP digit is valid for any input; when the sample shows it constant or too
+		// skewed to balance, key ranges (splitters over whole derived keys, equally valid for any
+		// input) take over.  Only an input whose sampled keys are all equal goes to the exact path,
+		// which knows how to leave constant shards where they are.
+		bool go = tot != 0;
+		rsx_route route;
+		memset(&route, 0, sizeof(route));
+		if (go && (r = rsx_multi_route(hall.data(), world, cols, rank, (flags & RSX_MULTI_NO_KEY_RANGE) ? 1e30 : 1.15, &route)))
+			return r;
+		const bool top_constant = mx == tot;
+		uint64_t splitters[RSX_MAX_RANKS] = {};
+		int nsplit = 0;
+		if (go && (top_constant || route.key_range)) {
+			if (world - 1 > 15) {
+				go = false;
+			} else {
 				constexpr size_t kSamples = 8192;
 				std::vector<uint64_t> mine(1 + kSamples, ~0ULL), all((1 + kSamples) * world);
 				const size_t cnt = std::min(kSamples, n);
@@ -288,14 +293,24 @@ int rsx_sort_shard(const rsx_comm *comm, const rsx_shard_ops *ops_in, void *src,
 					const uint64_t *pq = &all[(size_t)q * (1 + kSamples)];
 					pooled.insert(pooled.end(), pq + 1, pq + 1 + pq[0]);
 				}
-				nsplit = world - 1;
-				rsx_multi_splitters(pooled.data(), pooled.size(), world, splitters);
-				rep->key_range = 1;
-			} else {
-				rep->routing_column = route.routing_column;
+				if (pooled.empty() || *std::min_element(pooled.begin(), pooled.end()) == *std::max_element(pooled.begin(), pooled.end())) {
+					go = false; // (nearly) constant keys: the exact path decides
+				} else {
+					nsplit = world - 1;
+					rsx_multi_splitters(pooled.data(), pooled.size(), world, splitters);
+					rep->key_range = 1;
+				}
 			}
+		}
+		if (go) {
+			rep->live_mask = 1u << (cols - 1);
+			rep->n_total = n_total;
+			if (!rep->key_range)
+				rep->routing_column = route.routing_column;
+			rep->seconds_histogram = since(t0);
+			t0 = clk::now();
 			// room for the estimated shard + sampling error; every rank reaches the same verdict
-			const double est = route.key_range ? (double)n_total / world : (double)route.max_n_out / (double)std::max<uint64_t>(tot, 1) * (double)n_total;
+			const double est = rep->key_range ? (double)n_total / world : (double)route.max_n_out / (double)std::max<uint64_t>(tot, 1) * (double)n_total;
 			rep->needed_capacity = (uint64_t)(std::max(est * 1.03, (double)n_max)) + 4096;
 			if (rep->needed_capacity > cap_min)
 				return RSX_ERR_WORKSPACE;
