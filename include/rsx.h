@@ -143,6 +143,9 @@ int rsx_scatter_pass_append(const void *src, size_t n, const rsx_layout *layout,
                             uint32_t *overflow_out, void *stream);
 int rsx_histogram_column_sampled(const void *src, size_t n, const rsx_layout *layout, int col, size_t stride,
                                  uint64_t *hist_out /* 256 */, void *stream);
+/* DERIVED keys of `count` (<= 2048) evenly spaced records, record i * (n / count): the sample the
+ * key-range splitters are quantiles of.  `derived_out` is a HOST array. */
+int rsx_sample_keys(const void *src, size_t n, const rsx_layout *layout, size_t count, uint64_t *derived_out, void *stream);
 
 /* Key-range routing for skewed multi-GPU inputs (sample-sort style): `splitters` are nsplit
  * (<= 15) ascending DERIVED keys; a record's destination is the number of splitters <= its

@@ -1429,6 +1429,35 @@ int rsx_scatter_pass_append(const void *src, size_t n, const rsx_layout *layout,
 	return RSX_OK;
 }
 
+// `count` evenly spaced records' DERIVED keys (record i * (n / count)), HOST output: the sample the
+// key-range splitters are quantiles of.  count <= 8192.
+int rsx_sample_keys(const void *src, size_t n, const rsx_layout *layout, size_t count, uint64_t *derived_out, void *stream) {
+	KeyDesc kd;
+	int r = check_layout(layout, &kd);
+	if (r)
+		return r;
+	if (!src || !derived_out || count < 1 || count > n || count > kMaxCols * kBins)
+		return RSX_ERR_INVALID;
+	int dev;
+	if ((r = current_device(&dev)))
+		return r;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	Plan P;
+	rsx_layout l1 = *layout;
+	make_plan(P, 2, &l1, kd, 0);
+	Lease L;
+	if ((r = acquire(L, dev, P.total)))
+		return r;
+	L.enqueued(st);
+	WsHead *ws = reinterpret_cast<WsHead *>(static_cast<unsigned char *>(L.ptr) + P.off_head);
+	CU(launch_sample_keys(src, count, n / count, layout->record_bytes, kd, ws->offs, st)); // offs: 16 KB of scratch in the head
+	CU(cudaMemcpyAsync(L.readback(), ws->offs, sizeof(uint64_t) * count, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	L.drained();
+	memcpy(derived_out, L.readback(), sizeof(uint64_t) * count);
+	return RSX_OK;
+}
+
 // The 256-bin histogram of one column over a SAMPLE of the records (every stride-th one): what
 // the append-mode exchange balances its bucket ranges with.
 int rsx_histogram_column_sampled(const void *src, size_t n, const rsx_layout *layout, int col, size_t stride,

@@ -130,6 +130,8 @@ cudaError_t launch_iota_if_early(void *index_buffer, int idx_bytes, size_t n, co
 cudaError_t launch_narrow_index(const uint32_t *wide0, const uint32_t *wide1, void *index_buffer,
                                 int idx_bytes, size_t n, const Ctl *ctl, cudaStream_t st);
 
+cudaError_t launch_sample_keys(const void *data, size_t count, size_t stride, uint32_t record_bytes, const KeyDesc &kd,
+                               unsigned long long *d_out, cudaStream_t st);
 cudaError_t launch_sample_column_hist(const void *data, size_t n, uint32_t record_bytes, const KeyDesc &kd, int col, size_t stride,
                                       unsigned long long *d_hist, int num_sms, cudaStream_t st);
 

@@ -75,19 +75,7 @@ int cuda_hist(void *, const void *src, size_t n, const rsx_layout *L, uint64_t *
 int cuda_sample(void *, const void *src, size_t n, const rsx_layout *L, size_t count, uint64_t *derived, void *stream) {
 	if (count == 0)
 		return RSX_OK;
-	// evenly spaced records: index i*n/count; gathered with one strided 2-D copy when the stride is
-	// uniform (n a multiple of count is not required: use floor(n/count) as the stride)
-	const size_t stride = n / count; // >= 1 because count <= n
-	std::vector<unsigned char> buf(count * L->record_bytes);
-	cudaError_t e = cudaMemcpy2DAsync(buf.data(), L->record_bytes, src, stride * L->record_bytes, L->record_bytes, count,
-	                                  cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream));
-	if (e == cudaSuccess)
-		e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
-	if (e != cudaSuccess)
-		return RSX_ERR_CUDA;
-	for (size_t i = 0; i < count; ++i)
-		derived[i] = derive_host(buf.data() + i * L->record_bytes, *L);
-	return RSX_OK;
+	return rsx_sample_keys(src, n, L, count, derived, stream); // record i * (n / count), i < count
 }
 
 int cuda_split_counts(void *, const void *src, size_t n, const rsx_layout *L, const uint64_t *split, int nsplit,
@@ -280,7 +268,7 @@ int rsx_sort_shard(const rsx_comm *comm, const rsx_shard_ops *ops_in, void *src,
 			if (world - 1 > 15) {
 				go = false;
 			} else {
-				constexpr size_t kSamples = 8192;
+				constexpr size_t kSamples = 2048;
 				std::vector<uint64_t> mine(1 + kSamples, ~0ULL), all((1 + kSamples) * world);
 				const size_t cnt = std::min(kSamples, n);
 				mine[0] = cnt;
@@ -443,7 +431,7 @@ int rsx_sort_shard(const rsx_comm *comm, const rsx_shard_ops *ops_in, void *src,
 	uint64_t send_counts[RSX_MAX_RANKS], recv_counts[RSX_MAX_RANKS], dest_offset[RSX_MAX_RANKS];
 	uint64_t my_n_out = route.n_out, max_n_out = route.max_n_out;
 	if (route.key_range && world - 1 <= 15) {
-		constexpr size_t kSamples = 8192;
+		constexpr size_t kSamples = 2048;
 		std::vector<uint64_t> mine(1 + kSamples, ~0ULL), all((1 + kSamples) * world);
 		const size_t cnt = std::min(kSamples, n);
 		mine[0] = cnt;

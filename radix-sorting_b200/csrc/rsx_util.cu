@@ -234,6 +234,15 @@ __global__ void gather_records_kernel(const W *__restrict__ src, const I *__rest
 	}
 }
 
+// out[i] = derived key of record i * stride (key-range routing: the splitters are quantiles of a sample)
+template <int ES>
+__global__ void sample_keys_kernel(const typename Rec<ES>::type *__restrict__ data, size_t count, size_t stride, KeyDesc kd,
+                                   unsigned long long *out) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count)
+		out[i] = derive_key(key_word<ES>(data[i * stride], kd.word_sel), kd);
+}
+
 // Digit histogram of column `col` over every stride-th record (append-mode routing estimate).
 template <int ES>
 __global__ void sample_column_hist_kernel(const typename Rec<ES>::type *__restrict__ data, size_t n, KeyDesc kd, uint32_t col,
@@ -358,6 +367,21 @@ cudaError_t launch_extract_keys(const void *recs, size_t n, uint32_t record_byte
 	case 2: extract_keys_kernel<<<g, 256, 0, st>>>(r, n, record_bytes, key_offset, static_cast<uint16_t *>(keys_out)); break;
 	case 4: extract_keys_kernel<<<g, 256, 0, st>>>(r, n, record_bytes, key_offset, static_cast<uint32_t *>(keys_out)); break;
 	case 8: extract_keys_kernel<<<g, 256, 0, st>>>(r, n, record_bytes, key_offset, static_cast<unsigned long long *>(keys_out)); break;
+	default: return cudaErrorInvalidValue;
+	}
+	count_launch();
+	return cudaGetLastError();
+}
+
+cudaError_t launch_sample_keys(const void *data, size_t count, size_t stride, uint32_t record_bytes, const KeyDesc &kd,
+                               unsigned long long *d_out, cudaStream_t st) {
+	const int g = (int)((count + 255) / 256);
+	switch (record_bytes) {
+	case 1: sample_keys_kernel<1><<<g, 256, 0, st>>>(static_cast<const uint8_t *>(data), count, stride, kd, d_out); break;
+	case 2: sample_keys_kernel<2><<<g, 256, 0, st>>>(static_cast<const uint16_t *>(data), count, stride, kd, d_out); break;
+	case 4: sample_keys_kernel<4><<<g, 256, 0, st>>>(static_cast<const uint32_t *>(data), count, stride, kd, d_out); break;
+	case 8: sample_keys_kernel<8><<<g, 256, 0, st>>>(static_cast<const unsigned long long *>(data), count, stride, kd, d_out); break;
+	case 16: sample_keys_kernel<16><<<g, 256, 0, st>>>(static_cast<const ulonglong2 *>(data), count, stride, kd, d_out); break;
 	default: return cudaErrorInvalidValue;
 	}
 	count_launch();
