@@ -233,6 +233,7 @@ typedef struct rsx_multi_report {
 #define RSX_MULTI_NO_KEY_RANGE 2u /* always route by bucket ranges (tests)                  */
 #define RSX_MULTI_FULL_HISTOGRAM 4u /* count every column for routing, not just the top one (tests) */
 #define RSX_MULTI_EXACT 8u        /* keys-only records too take the exact (histogram + offsets) exchange */
+#define RSX_MULTI_APPEND 16u      /* keys-only records append even where the cursor contention heuristic says no */
 
 int rsx_multi_route(const uint64_t *hist_all /* [world][cols][256] */, int world, int cols, int rank,
                     double skew_threshold, rsx_route *out);

@@ -290,6 +290,14 @@ int rsx_sort_shard(const rsx_comm *comm, const rsx_shard_ops *ops_in, void *src,
 				}
 			}
 		}
+		// Every (tile, destination) run costs one atomic on the destination's cursor: world x tiles
+		// of them per cursor.  Measured on 8 GPUs with 4-byte keys (780 K atomics per cursor in a
+		// 5 ms pass) the cursor becomes the bottleneck (exchange 7.1 ms vs 5.3 ms exact), with
+		// 8-byte keys (half the tiles per byte) and at 2 GPUs it does not: bucket-range routing
+		// appends only while world <= record_bytes; key-range routing always does (it also saves
+		// the counting pass, which outweighs the contention: config 5 zipf 87 -> 66 ms on 8 GPUs).
+		if (go && !rep->key_range && world > (int)rb && !(flags & RSX_MULTI_APPEND))
+			go = false;
 		if (go) {
 			rep->live_mask = 1u << (cols - 1);
 			rep->n_total = n_total;
