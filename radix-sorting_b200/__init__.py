@@ -147,6 +147,13 @@ def _lib() -> C.CDLL:
         L.rsx_split_counts.argtypes = [vp, sz, LP, u64p, C.c_int, u64p, vp]
         L.rsx_split_pass_to.restype = C.c_int
         L.rsx_split_pass_to.argtypes = [vp, sz, LP, u64p, C.c_int, u64p, vp]
+    L.rsx_scatter_pass_append.restype = C.c_int
+    L.rsx_scatter_pass_append.argtypes = [vp, sz, LP, C.c_int, C.POINTER(C.c_uint8), u64p, C.c_int, u64p, u64p, u64p, C.c_int,
+                                          C.POINTER(C.c_uint32), vp]
+    L.rsx_histogram_column_sampled.restype = C.c_int
+    L.rsx_histogram_column_sampled.argtypes = [vp, sz, LP, C.c_int, sz, u64p, vp]
+    L.rsx_sample_keys.restype = C.c_int
+    L.rsx_sample_keys.argtypes = [vp, sz, LP, sz, u64p, vp]
     L.rsx_multi_route.restype = C.c_int
     L.rsx_multi_route.argtypes = [u64p, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(RsxRoute)]
     L.rsx_multi_splitters.restype = C.c_int

@@ -423,6 +423,75 @@ def test_scatter_pass_to_destinations(rsx, torch, oracle, tname, col):
         assert res.cpu().numpy().tobytes() == want.tobytes(), f"destination {d}"
 
 
+@pytest.mark.parametrize("tname,col", [("u32", 3), ("u64", 7), ("f32", 3), ("i64", -1), ("u32", -1)])
+def test_scatter_pass_append(rsx, torch, tname, col):
+    """rsx_scatter_pass_append (keys-only multi-GPU exchange without a routing histogram) with three
+    local 'destinations': every destination's append cursor ends at the number of keys it owns and
+    its buffer holds exactly those keys (as a multiset: the landing order of runs is arbitrary);
+    a destination that is too small raises the overflow flag and is not written beyond its capacity."""
+    import ctypes as C
+    import importlib
+    dsort = importlib.import_module("radix-sorting_b200.dist")
+    t = TYPES[tname]
+    n = 1_500_007
+    data = make_input(tname, n, 91, "uniform" if col >= 0 else "zipf")
+    L = rsx.RsxLayout(t.record_bytes, 0, t.key_bytes, t.kdf_kind, 0)
+    derived = dsort.derive_np(np.ascontiguousarray(data).view(np.uint8).reshape(n, t.record_bytes), L)
+    owner = np.zeros(256, dtype=np.uint8)
+    owner[40:200] = 1
+    owner[200:] = 2
+    if col >= 0:
+        dest = owner[((derived >> np.uint64(8 * col)) & np.uint64(0xFF)).astype(np.int64)].astype(np.int64)
+        splitters = []
+    else:
+        splitters = dsort.choose_splitters(derived[::53], 3)
+        dest = np.searchsorted(np.array(splitters, dtype=np.uint64), derived, side="right")
+    counts = [int((dest == d).sum()) for d in range(3)]
+    src = to_dev(torch, data)
+    u = f"<u{t.record_bytes}"
+    for shrink in (False, True):
+        caps = [c + 1000 for c in counts]
+        if shrink:
+            caps[1] = counts[1] // 2  # destination 1 cannot take its share
+        bufs = [torch.full((max(c, 1) * t.record_bytes + 64,), 0xAB, dtype=torch.uint8, device="cuda") for c in caps]
+        cursors = torch.zeros(3, dtype=torch.int64, device="cuda")
+        base = (C.c_uint64 * 3)(*[b.data_ptr() for b in bufs])
+        cur = (C.c_uint64 * 3)(*[cursors.data_ptr() + 8 * d for d in range(3)])
+        cap = (C.c_uint64 * 3)(*caps)
+        own = (C.c_uint8 * 256)(*owner.tolist())
+        sp = (C.c_uint64 * max(len(splitters), 1))(*splitters) if splitters else None
+        ovf = C.c_uint32(7)
+        st = rsx.lib().rsx_scatter_pass_append(src.data_ptr(), n, C.byref(L), col, own, sp, len(splitters), base, cur, cap, 3,
+                                               C.byref(ovf), None)
+        assert st == 0, st
+        torch.cuda.synchronize()
+        got_counts = cursors.cpu().tolist()
+        if not shrink:
+            assert ovf.value == 0 and got_counts == counts
+            for d in range(3):
+                got = bufs[d][: counts[d] * t.record_bytes].cpu().numpy().view(u)
+                assert np.array_equal(np.sort(got), np.sort(data[dest == d].view(u))), f"destination {d}"
+                assert bool((bufs[d][counts[d] * t.record_bytes:] == 0xAB).all())
+        else:
+            assert ovf.value == 1
+            assert bool((bufs[1][caps[1] * t.record_bytes:] == 0xAB).all()), "written beyond the stated capacity"
+
+
+def test_sampled_histogram_and_key_sample(rsx, torch):
+    import ctypes as C
+    n, stride = 1_000_003, 37
+    data = make_input("u32", n, 5, "and2")
+    src = to_dev(torch, data)
+    L = rsx.RsxLayout(4, 0, 4, 0, 0)
+    out = np.zeros(256, dtype=np.uint64)
+    assert rsx.lib().rsx_histogram_column_sampled(src.data_ptr(), n, C.byref(L), 2, stride,
+                                                  out.ctypes.data_as(C.POINTER(C.c_uint64)), None) == 0
+    assert np.array_equal(out, np.bincount((data[::stride] >> 16) & 0xFF, minlength=256).astype(np.uint64))
+    keys = np.zeros(2048, dtype=np.uint64)
+    assert rsx.lib().rsx_sample_keys(src.data_ptr(), n, C.byref(L), 2048, keys.ctypes.data_as(C.POINTER(C.c_uint64)), None) == 0
+    assert np.array_equal(keys, data[np.arange(2048) * (n // 2048)].astype(np.uint64))
+
+
 def test_more_than_2_pow_32_records(rsx, torch):
     """n >= 2^32 -- the reference's 64-bit counter tier (radix_sort.hpp:111-113): 4.3 G one-byte
     keys, one live column, result in aux; checked by descents + multiset checksum."""
