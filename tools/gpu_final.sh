@@ -9,7 +9,6 @@ timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_
 timeout 600 python bench.py --impl reference > gpurun_out/bench_reference.json 2>&1; tail -c 300 gpurun_out/bench_reference.json; echo
 timeout 600 python bench.py --sweep > gpurun_out/sweep.json 2> gpurun_out/sweep.err; tail -c 300 gpurun_out/sweep.json; echo
 timeout 900 python tools/bench_configs.py > gpurun_out/configs.log 2>&1; tail -3 gpurun_out/configs.log
-timeout 600 python tools/footprints.py 0 > gpurun_out/footprints.log 2>&1; tail -3 gpurun_out/footprints.log
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-extra --workload 256M-u32-uniform > gpurun_out/ncu_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:scatter_kernel -s 4 -c 1 -o gpurun_out/prof_scatter_u32 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-extra --workload 256M-u32-uniform > gpurun_out/ncu_full.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:histogram_kernel -s 1 -c 1 -o gpurun_out/prof_hist_u32 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-extra --workload 256M-u32-uniform > gpurun_out/ncu_full_hist.log 2>&1
