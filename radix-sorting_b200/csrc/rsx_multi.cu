@@ -220,15 +220,13 @@ int rsx_sort_shard(const rsx_comm *comm, const rsx_shard_ops *ops_in, void *src,
 	// destination's append cursor, and the full routing histogram pass (and, for skewed keys, the
 	// counting pass) disappears.  Anything else takes the exact path below.
 	if (!ops_in && recv_peers && !(flags & (RSX_MULTI_NO_FUSED | RSX_MULTI_EXACT)) && L->record_bytes == L->key_bytes &&
-	    cols > 1 && world > 1 && capacity * rb >= 64) {
-		const uint64_t coff = ((capacity * rb) & ~(uint64_t)15) - 16; // the cursor: last aligned 16 bytes of the receive buffer
-		const uint64_t cap_eff = coff / rb;
+	    cols > 1 && world > 1 && capacity * rb >= 4096) {
 		const size_t stride = std::max<size_t>(1, n / 131072);
 		std::vector<uint64_t> h(256 + 2), g((256 + 2) * (size_t)world);
 		if (n && (r = rsx_histogram_column_sampled(src, n, L, cols - 1, stride, h.data(), stream)))
 			return r;
 		h[256] = n;
-		h[257] = cap_eff;
+		h[257] = capacity;
 		if ((r = comm->allgather(comm->ctx, h.data(), g.data(), h.size() * sizeof(uint64_t))))
 			return r;
 		const size_t hw = (size_t)cols * 256;
@@ -252,6 +250,11 @@ int rsx_sort_shard(const rsx_comm *comm, const rsx_shard_ops *ops_in, void *src,
 			tot += colsum[b];
 			mx = std::max(mx, colsum[b]);
 		}
+		// the cursor of every rank sits at the SAME offset of its receive buffer (the last aligned
+		// 16 bytes of the smallest one), so that every rank can address every cursor
+		const uint64_t coff = ((cap_min * rb) & ~(uint64_t)15) - 16;
+		const uint64_t cap_eff = coff / rb;
+		cap_min = cap_eff;
 		// Routing by the TOP digit is valid for any input; when the sample shows it constant or too
 		// skewed to balance, key ranges (splitters over whole derived keys, equally valid for any
 		// input) take over.  Only an input whose sampled keys are all equal goes to the exact path,
@@ -265,7 +268,7 @@ int rsx_sort_shard(const rsx_comm *comm, const rsx_shard_ops *ops_in, void *src,
 		uint64_t splitters[RSX_MAX_RANKS] = {};
 		int nsplit = 0;
 		if (go && (top_constant || route.key_range)) {
-			if (world - 1 > 15) {
+			if (world - 1 > 15 || (flags & RSX_MULTI_NO_KEY_RANGE)) {
 				go = false;
 			} else {
 				constexpr size_t kSamples = 2048;

@@ -206,7 +206,7 @@ def partitioned_sort(keys, kf, group=None, n: Optional[int] = None, ops=None, fu
     capacity = count  # records the caller's tensor can hold
     src = keys
     rep = rsx.RsxMultiReport()
-    for attempt in range(2):
+    for attempt in range(3):
         cap_elems = capacity * rec_elems
         symm = _symmetric_recv(cap_elems, keys, group) if (fused and on_gpu) else None
         if fused and on_gpu:  # every rank must take the same branch
@@ -230,10 +230,10 @@ def partitioned_sort(keys, kf, group=None, n: Optional[int] = None, ops=None, fu
         st = lib.rsx_sort_shard(C.byref(comm), C.byref(ops) if ops is not None else None, src.data_ptr(), n, recv.data_ptr(), peers, capacity, C.byref(L),
                                 flags | (0 if symm is not None else rsx.MULTI_NO_FUSED), C.byref(res_ptr), C.byref(n_out),
                                 C.byref(rep), stream)
-        if st == rsx.RSX_ERR_WORKSPACE and attempt == 0:
+        if st == rsx.RSX_ERR_WORKSPACE and attempt < 2:
             # the routed sizes need more room than the tensors have (same verdict on every rank,
             # nothing was moved yet): grow once, with some slack for the next calls
-            capacity = int(rep.needed_capacity * 1.03) + 1024
+            capacity = max(int(rep.needed_capacity * 1.03) + 1024, capacity + 1)
             skey = (keys.dtype, dev.index if on_gpu else -1)
             cur = _Buffers.src.get(skey)
             if cur is None or cur.numel() < capacity * rec_elems:
