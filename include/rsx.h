@@ -278,6 +278,13 @@ int rsx_fill_keys(void *dst, size_t count, int key_bytes, uint64_t seed, uint64_
 int rsx_verify(const void *data, size_t n, const rsx_layout *layout, uint64_t *descents_out,
                uint64_t *sum_out, uint64_t *xor_out, void *stream);
 
+/* The key-compaction plan (README.md:716-758) for the OR of all derived keys and the OR of their
+ * complements: up to 8 runs {src_shift, width, dst_shift} of varying bits gathered into a narrower
+ * key, and the constant bits.  Pure host arithmetic.  Returns the number of 8-bit passes the
+ * compacted key needs, 0 if compaction would not pay, or a negative rsx_status. */
+int rsx_plan_compaction(uint64_t key_or, uint64_t key_nand, int key_bytes, int live_columns,
+                        uint32_t *runs_out /* 24 */, uint64_t *const_bits_out);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 const char *rsx_strerror(int status);
 const char *rsx_last_cuda_error(void); /* thread-local text of the last failing CUDA call */

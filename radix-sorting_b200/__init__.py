@@ -36,7 +36,7 @@ RSX_ERR_WORKSPACE, RSX_ERR_IDX_RANGE, RSX_ERR_MIXED_MEMORY = -4, -5, -6
 #: every symbol include/rsx.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "rsx_sort", "rsx_sort_rank", "rsx_histogram", "rsx_histogram_column", "rsx_scatter_pass", "rsx_scatter_pass_to",
-    "rsx_split_counts", "rsx_split_pass_to", "rsx_scatter_pass_append", "rsx_histogram_column_sampled", "rsx_sample_keys",
+    "rsx_split_counts", "rsx_split_pass_to", "rsx_scatter_pass_append", "rsx_histogram_column_sampled", "rsx_sample_keys", "rsx_plan_compaction",
     "rsx_multi_route", "rsx_multi_splitters", "rsx_sort_shard", "rsx_sort_multi",
     "rsx_workspace_bytes",
     "rsx_reserve", "rsx_release", "rsx_fill_keys", "rsx_verify", "rsx_strerror",
@@ -154,6 +154,8 @@ def _lib() -> C.CDLL:
     L.rsx_histogram_column_sampled.argtypes = [vp, sz, LP, C.c_int, sz, u64p, vp]
     L.rsx_sample_keys.restype = C.c_int
     L.rsx_sample_keys.argtypes = [vp, sz, LP, sz, u64p, vp]
+    L.rsx_plan_compaction.restype = C.c_int
+    L.rsx_plan_compaction.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint32), u64p]
     L.rsx_multi_route.restype = C.c_int
     L.rsx_multi_route.argtypes = [u64p, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(RsxRoute)]
     L.rsx_multi_splitters.restype = C.c_int

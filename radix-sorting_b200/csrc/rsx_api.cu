@@ -1490,6 +1490,33 @@ int rsx_histogram_column_sampled(const void *src, size_t n, const rsx_layout *la
 	return RSX_OK;
 }
 
+// The key-compaction plan for given OR / NAND masks (pure host arithmetic; tests/test_abi.py checks
+// it against a bit-level model without a device).  runs_out: up to 8 x {src_shift, width, dst_shift}.
+// Returns the number of compacted passes (0: compaction would not pay) or a negative rsx_status.
+int rsx_plan_compaction(uint64_t key_or, uint64_t key_nand, int key_bytes, int live_columns, uint32_t *runs_out,
+                        uint64_t *const_bits_out) {
+	if (!(key_bytes == 4 || key_bytes == 8) || live_columns < 0 || live_columns > key_bytes)
+		return RSX_ERR_INVALID;
+	Ctl c{};
+	c.key_or = key_or;
+	c.key_nand = key_nand;
+	c.ncols = (uint32_t)live_columns;
+	KeyDesc kd{};
+	kd.key_bytes = (uint32_t)key_bytes;
+	Compaction cmp{};
+	if (!plan_compaction(c, kd, &cmp))
+		return 0;
+	if (runs_out)
+		for (uint32_t i = 0; i < (uint32_t)kMaxRuns; ++i) {
+			runs_out[3 * i] = i < cmp.nruns ? cmp.src_shift[i] : 0;
+			runs_out[3 * i + 1] = i < cmp.nruns ? cmp.width[i] : 0;
+			runs_out[3 * i + 2] = i < cmp.nruns ? cmp.dst_shift[i] : 0;
+		}
+	if (const_bits_out)
+		*const_bits_out = cmp.const_bits;
+	return (int)((cmp.bits + 7) / 8);
+}
+
 // ---- bench helpers ---------------------------------------------------------------------------------
 int rsx_fill_keys(void *dst, size_t count, int key_bytes, uint64_t seed, uint64_t start, int dist,
                   uint64_t mask, uint64_t orv, void *stream) {

@@ -104,3 +104,52 @@ def test_workspace_sizing_and_options_need_no_device(rsx):
     assert L.rsx_set_option(b"rank_mode", 7) == rsx.RSX_ERR_INVALID
     assert L.rsx_set_option(b"no_such_option", 1) == rsx.RSX_ERR_INVALID
     assert L.rsx_set_option(b"scatter_variant", 0) == 0 and L.rsx_set_option(b"rank_mode", -1) == 0
+
+
+def test_key_compaction_plan_is_order_preserving(rsx):
+    """rsx_plan_compaction (host arithmetic of N4): the runs cover every varying bit, gather them in
+    order (so comparing compacted keys == comparing original keys), scatter back exactly, and the
+    plan is refused unless it saves enough passes.  Bit-level model in numpy, no device."""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    L = rsx.lib()
+    for kb in (4, 8):
+        full = (1 << (8 * kb)) - 1
+        for trial in range(300):
+            nbits = int(rng.integers(1, 8 * kb // 2))
+            varying = 0
+            for b in rng.choice(8 * kb, size=nbits, replace=False):
+                varying |= 1 << int(b)
+            const_ones = int(rng.integers(0, 1 << 62)) & full & ~varying
+            key_or, key_nand = varying | const_ones, (varying | (~const_ones & full)) & full
+            live = sum(1 for c in range(kb) if (varying >> (8 * c)) & 0xFF)
+            runs = (C.c_uint32 * 24)()
+            cb = C.c_uint64(0)
+            passes = L.rsx_plan_compaction(key_or, key_nand, kb, live, runs, C.byref(cb))
+            assert passes >= 0
+            if passes == 0:
+                continue
+            need = 3 if kb == 4 else 2
+            assert passes + need <= live, (hex(varying), passes, live)
+            rr = [(runs[3 * i], runs[3 * i + 1], runs[3 * i + 2]) for i in range(8) if runs[3 * i + 1]]
+            covered = 0
+            at = 0
+            for s_, w_, d_ in rr:
+                assert d_ == at and w_ >= 1 and not (covered >> s_), "runs ascending, packed without gaps"
+                covered |= ((1 << w_) - 1) << s_
+                at += w_
+            assert covered & varying == varying and passes == (at + 7) // 8
+            assert cb.value == (const_ones & ~covered)
+
+            def compact(k):
+                return sum(((k >> s_) & ((1 << w_) - 1)) << d_ for s_, w_, d_ in rr)
+
+            def expand(v):
+                return cb.value | sum(((v >> d_) & ((1 << w_) - 1)) << s_ for s_, w_, d_ in rr)
+
+            keys = [const_ones | (int(rng.integers(0, 1 << 62)) & varying) for _ in range(40)]
+            for a in keys:
+                assert expand(compact(a)) == a
+            srt = sorted(keys)
+            assert sorted(keys, key=compact) == srt or [compact(k) for k in sorted(keys, key=compact)] == [compact(k) for k in srt]
+    assert L.rsx_plan_compaction(0xFF, 0xFF, 3, 1, None, None) == rsx.RSX_ERR_INVALID
