@@ -607,11 +607,15 @@ extern "C" int rsx_sort_multi(int ngpus, const int *devices, void *const *src, v
 	for (int g = 0; g < ngpus; ++g)
 		if (n[g] > capacity || (capacity && (!src[g] || !aux[g])))
 			return RSX_ERR_INVALID;
+	int caller_device = 0;
+	cudaGetDevice(&caller_device); // restored before returning: the calling thread's device is not ours to change
 	// peer mappings: every device stores into every other device's receive buffer
 	bool peers_ok = true;
 	for (int g = 0; g < ngpus && peers_ok; ++g) {
-		if (cudaSetDevice(devices[g]) != cudaSuccess)
+		if (cudaSetDevice(devices[g]) != cudaSuccess) {
+			cudaSetDevice(caller_device);
 			return RSX_ERR_NO_DEVICE;
+		}
 		for (int d = 0; d < ngpus; ++d) {
 			if (d == g || devices[d] == devices[g])
 				continue;
@@ -627,6 +631,7 @@ extern "C" int rsx_sort_multi(int ngpus, const int *devices, void *const *src, v
 			(void)cudaGetLastError();
 		}
 	}
+	cudaSetDevice(caller_device);
 	if (!peers_ok)
 		return RSX_ERR_CUDA; // no NVLink / P2P between the devices: use the torchrun + NCCL path (dist.py)
 	ThreadGroup grp(ngpus);
