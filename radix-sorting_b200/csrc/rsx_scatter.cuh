@@ -191,9 +191,13 @@ template <int ES> __device__ __forceinline__ typename Rec<ES>::type make_pad(con
 //      hence the same stable order):                                2 ATOMS per record, no rank registers
 // ELB: the first look-back window is LOADED before the placement sweep and evaluated after it, so
 //      its L2 round trip overlaps the placement instead of following it.
-template <int T, int I, int MB, int LBK, bool ST, int MD = 0, bool ELB = false> struct CfgT {
+// SLB: split look-back -- the digit threads (warps 0-7) walk the look-back chain right after the
+//      digit scan, WHILE warps 8.. place their records, and place their own afterwards: the chain's
+//      L2 round trips overlap the placement, and this tile's inclusive prefix is published one
+//      placement phase earlier (which shortens every successor's chain).
+template <int T, int I, int MB, int LBK, bool ST, int MD = 0, bool ELB = false, bool SLB = false> struct CfgT {
 	static constexpr int kThreads = T, kItems = I, kMinBlocks = MB, kLookback = LBK, kMode = MD;
-	static constexpr bool kStage = ST, kEarlyLookback = ELB;
+	static constexpr bool kStage = ST, kEarlyLookback = ELB, kSplitLookback = SLB;
 };
 
 // Predicated shared-memory ticket: lanes with skip == true keep `r` (their vote-derived rank).
@@ -246,12 +250,12 @@ template <> struct ScatterCfgV<4, 0, 4> : CfgT<512, 40, 1, 8, true> {};
 template <> struct ScatterCfgV<4, 0, 5> : CfgT<512, 44, 1, 8, true> {};
 template <> struct ScatterCfgV<4, 0, 6> : CfgT<512, 22, 2, 8, true, 0, true> {};
 template <> struct ScatterCfgV<4, 0, 7> : CfgT<512, 22, 2, 8, true, 1, false> {};
-template <> struct ScatterCfgV<4, 0, 8> : CfgT<512, 22, 2, 8, true, 1, true> {};
-template <> struct ScatterCfgV<4, 0, 9> : CfgT<512, 22, 2, 16, true, 1, true> {};
+template <> struct ScatterCfgV<4, 0, 8> : CfgT<512, 22, 2, 8, true, 0, false, true> {};
+template <> struct ScatterCfgV<4, 0, 9> : CfgT<512, 22, 2, 16, true, 0, false, true> {};
 template <> struct ScatterCfgV<8, 0, 6> : CfgT<512, 24, 1, 8, true, 0, true> {};
 template <> struct ScatterCfgV<8, 0, 7> : CfgT<512, 24, 1, 8, true, 1, false> {};
-template <> struct ScatterCfgV<8, 0, 8> : CfgT<512, 24, 1, 8, true, 1, true> {};
-template <> struct ScatterCfgV<8, 0, 9> : CfgT<512, 24, 1, 16, true, 1, true> {};
+template <> struct ScatterCfgV<8, 0, 8> : CfgT<512, 24, 1, 8, true, 0, false, true> {};
+template <> struct ScatterCfgV<8, 0, 9> : CfgT<512, 24, 1, 16, true, 0, false, true> {};
 template <> struct ScatterCfgV<8, 0, 1> : CfgT<256, 24, 2, 8, true> {};
 template <> struct ScatterCfgV<8, 0, 2> : CfgT<384, 16, 2, 8, true> {};
 template <> struct ScatterCfgV<8, 0, 3> : CfgT<256, 24, 2, 16, true> {};
@@ -575,8 +579,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		RSX_T(4);
 
 		// ---- (3b, early) first look-back window: loads issued now, evaluated after the placement ----
-		constexpr bool kPair = THREADS >= 2 * kBins;
-		constexpr bool ELB = Cfg::kEarlyLookback;
+		constexpr bool SLB = Cfg::kSplitLookback && THREADS >= 2 * kBins;
+		constexpr bool kPair = THREADS >= 2 * kBins && !SLB;
+		constexpr bool ELB = Cfg::kEarlyLookback && !SLB;
 		const uint32_t dgt = tid & (kBins - 1), half = tid / kBins;
 		[[maybe_unused]] OffT lbw[LB];
 		if constexpr (ELB) {
@@ -589,32 +594,36 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 		}
 
 		// ---- 4. records / payloads to their tile-sorted slot ----
-		if constexpr (MODE == 0) {
+		auto place = [&]() {
+			if constexpr (MODE == 0) {
 #pragma unroll
-			for (int i = 0; i < ITEMS; ++i) { // fully unrolled on purpose: partial unrolling costs 10 %
-				const R r = s_stage[t0 + i * 32];
-				const uint32_t pos = wh[tile_digit<ES, DM>(p, r, dd)] + get_rank(i);
-				s_rec[pos] = r;
-				if constexpr (PL != 0)
-					s_pl[pos] = synth ? (P)(base + t0 + i * 32) : s_stage_pl[t0 + i * 32];
-			}
-		} else {
-			// same sweep order as the count: the ticket now returns the slot itself
-			uint32_t hotpos = wh[hot];
-			__syncwarp();
+				for (int i = 0; i < ITEMS; ++i) { // fully unrolled on purpose: partial unrolling costs 10 %
+					const R r = s_stage[t0 + i * 32];
+					const uint32_t pos = wh[tile_digit<ES, DM>(p, r, dd)] + get_rank(i);
+					s_rec[pos] = r;
+					if constexpr (PL != 0)
+						s_pl[pos] = synth ? (P)(base + t0 + i * 32) : s_stage_pl[t0 + i * 32];
+				}
+			} else {
+				// same sweep order as the count: the ticket now returns the slot itself
+				uint32_t hotpos = wh[hot];
+				__syncwarp();
 #pragma unroll
-			for (int i = 0; i < ITEMS; ++i) {
-				const R r = s_stage[t0 + i * 32];
-				const uint32_t d = tile_digit<ES, DM>(p, r, dd);
-				const bool is_hot = d == hot;
-				const uint32_t m = __ballot_sync(FULL, is_hot);
-				const uint32_t pos = ticket_unless(&wh[d], is_hot, hotpos + __popc(m & lt));
-				hotpos += __popc(m);
-				s_rec[pos] = r;
-				if constexpr (PL != 0)
-					s_pl[pos] = synth ? (P)(base + t0 + i * 32) : s_stage_pl[t0 + i * 32];
+				for (int i = 0; i < ITEMS; ++i) {
+					const R r = s_stage[t0 + i * 32];
+					const uint32_t d = tile_digit<ES, DM>(p, r, dd);
+					const bool is_hot = d == hot;
+					const uint32_t m = __ballot_sync(FULL, is_hot);
+					const uint32_t pos = ticket_unless(&wh[d], is_hot, hotpos + __popc(m & lt));
+					hotpos += __popc(m);
+					s_rec[pos] = r;
+					if constexpr (PL != 0)
+						s_pl[pos] = synth ? (P)(base + t0 + i * 32) : s_stage_pl[t0 + i * 32];
+				}
 			}
-		}
+		};
+		if (!SLB || tid >= kBins)
+			place();
 		RSX_T(5);
 
 		// ---- 3b. decoupled look-back, one chain per digit.  The first round is split over two
@@ -742,6 +751,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 					s_gadj[dgt] = (OffT)p.offs[dgt] + excl - (OffT)tstart;
 				}
 			}
+		}
+		if constexpr (SLB) {
+			if (tid < kBins)
+				place();
 		}
 		RSX_T(6);
 		if (tid == 0) // next ticket: claimed as late as possible (see above)
