@@ -86,15 +86,10 @@ def _gpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("tname,dist,mask", [("u32", "uniform", -1), ("u64", "uniform", -1), ("rec8_u32", "uniform", 0xFFFFF),
-                                              ("u32", "zipf", -1), ("f32", "uniform", -1), ("u64", "constant", -1)])
-def test_sort_multi_matches_oracle(rsx, oracle, tname, dist, mask):
-    """rsx_sort_multi (one process, a thread per GPU, fused peer stores) on 2+ GPUs == oracle."""
+def _sort_multi_vs_oracle(rsx, oracle, tname, dist, mask, devices):
+    """Ragged shards (one per entry of `devices`) through rsx_sort_multi; concatenated output == oracle."""
     import torch
-    ng = min(_gpus(), 4)
-    if ng < 2:
-        pytest.skip("needs >= 2 GPUs on one box (run with gpurun --gpus 2)")
+    ng = len(devices)
     t = TYPES[tname]
     n_per = [1_000_003, 700_001, 1_200_007, 5][:ng]  # ragged shards
     data = make_input(tname, sum(n_per), 606, dist, mask & ((1 << 64) - 1))
@@ -104,19 +99,19 @@ def test_sort_multi_matches_oracle(rsx, oracle, tname, dist, mask):
     for g in range(ng):
         raw = np.ascontiguousarray(data[off:off + n_per[g]]).view(np.uint8).reshape(-1)
         off += n_per[g]
-        b = torch.zeros(cap * t.record_bytes, dtype=torch.uint8, device=f"cuda:{g}")
-        b[: raw.shape[0]] = torch.from_numpy(raw.copy()).to(f"cuda:{g}")
+        b = torch.zeros(cap * t.record_bytes, dtype=torch.uint8, device=f"cuda:{devices[g]}")
+        b[: raw.shape[0]] = torch.from_numpy(raw.copy()).to(f"cuda:{devices[g]}")
         src.append(b)
         aux.append(torch.zeros_like(b))
     L = rsx.RsxLayout(t.record_bytes, t.key_offset, t.key_bytes, t.kdf_kind, 0)
-    devs = (C.c_int * ng)(*range(ng))
+    devs = (C.c_int * ng)(*devices)
     srcp = (C.c_void_p * ng)(*[b.data_ptr() for b in src])
     auxp = (C.c_void_p * ng)(*[b.data_ptr() for b in aux])
     ns = (C.c_size_t * ng)(*n_per)
     res = (C.c_void_p * ng)()
     nout = (C.c_size_t * ng)()
     reps = (rsx.RsxMultiReport * ng)()
-    for g in range(ng):
+    for g in set(devices):
         torch.cuda.synchronize(g)
     st = rsx.lib().rsx_sort_multi(ng, devs, srcp, auxp, ns, cap, C.byref(L), 0, res, nout, reps)
     assert st == 0, (st, rsx.lib().rsx_last_cuda_error())
@@ -134,6 +129,35 @@ def test_sort_multi_matches_oracle(rsx, oracle, tname, dist, mask):
         assert reps[0].fused == 1
         if mask == -1:
             assert reps[0].routing_column == t.key_bytes - 1
+    return reps
+
+
+_MULTI_CASES = [("u32", "uniform", -1), ("u64", "uniform", -1), ("rec8_u32", "uniform", 0xFFFFF),
+                ("u32", "zipf", -1), ("f32", "uniform", -1), ("u64", "constant", -1)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tname,dist,mask", _MULTI_CASES)
+def test_sort_multi_matches_oracle(rsx, oracle, tname, dist, mask):
+    """rsx_sort_multi (one process, a thread per GPU, fused peer stores) on 2+ GPUs == oracle."""
+    ng = min(_gpus(), 4)
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs on one box (run with gpurun --gpus 2)")
+    _sort_multi_vs_oracle(rsx, oracle, tname, dist, mask, list(range(ng)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tname,dist,mask", _MULTI_CASES)
+def test_sort_multi_with_every_shard_on_one_gpu(rsx, oracle, tname, dist, mask):
+    """The same orchestration with three shards that live on ONE device (devices = {0, 0, 0}): routing,
+    the fused partition + exchange (exact offsets for records, append cursors for keys) and the local
+    sorts run exactly as on three GPUs, only the "peer" stores stay on the device -- so the multi-GPU
+    path is covered on a single-GPU box too."""
+    reps = _sort_multi_vs_oracle(rsx, oracle, tname, dist, mask, [0, 0, 0])
+    if tname in ("u32", "u64", "f32") and dist != "constant":
+        assert reps[0].append == 1  # keys-only, world <= record_bytes (or key ranges): append mode
+    if tname == "rec8_u32":
+        assert reps[0].append == 0  # payloads: order-preserving exact offsets
 
 
 @pytest.mark.gpu
