@@ -38,6 +38,7 @@
 #pragma once
 
 #include "rsx_device.cuh"
+#include <type_traits>
 
 namespace rsx {
 
@@ -295,6 +296,11 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 	constexpr int TILE = SM::kTile;
 	constexpr int WARPS = SM::kWarps;
 	constexpr int LB = Cfg::kLookback;
+#ifdef RSX_WRITE_BATCH
+	constexpr int kWriteBatch = RSX_WRITE_BATCH;
+#else
+	constexpr int kWriteBatch = 2;
+#endif
 	constexpr uint32_t FULL = 0xFFFFFFFFu;
 	static_assert(THREADS >= kBins && THREADS % 32 == 0, "one digit thread per bin: the digit scan synchronises 256 threads");
 
@@ -836,28 +842,46 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter_kernel
 				}
 			}
 		} else if (full) {
-			// partial unroll: stores start flowing after a few loads instead of after all of them
-			// (1 B u32: 2.87 ms per pass vs 2.96 fully unrolled)
-#ifdef RSX_WRITE_UNROLL
-			constexpr int kWriteUnroll = RSX_WRITE_UNROLL;
-#else
-			constexpr int kWriteUnroll = (ITEMS % 5 == 0) ? 5 : 4;
-#endif
-#pragma unroll(kWriteUnroll)
-			for (int i = 0; i < ITEMS; ++i) {
-				const uint32_t s = tid + i * THREADS;
-				const R r = s_rec[s];
-				const OffT g = s_gadj[tile_digit<ES, DM>(p, r, dd)] + (OffT)s;
-				if constexpr (ES + PL <= 4) { // streaming (evict-first) stores: 1.4 % on 4-byte keys, neutral or worse on wider records
-					if (write_rec)
-						__stcs(out + g, r);
-				} else {
-					if (write_rec)
-						out[g] = r;
-					if constexpr (PL != 0)
-						pout[g] = s_pl[s];
+			// Batches of kWriteBatch records: a batch's tile loads, then its bucket-offset lookups, then
+			// its stores.  (A test of `write_rec` inside the loop makes the compiler branch around every
+			// store and serialises load -> lookup -> store per record, hence the two instantiations.)
+			// The pass is bound by shared-memory throughput, not by this latency chain: 1 B keys, ms per
+			// pass u32 / u64, serial 2.596 / 3.95, batches of 2: 2.580 / 3.87, 4: 2.637 / 3.93,
+			// 6: 2.66 / 3.96, 8: 2.66 / 4.62, 11: 2.61 / 5.29 (profiles/r2_write_batch.log).
+			auto write_full = [&](auto wr_tag) {
+				constexpr bool WR = decltype(wr_tag)::value;
+				constexpr int U = kWriteBatch;
+#pragma unroll 1
+				for (int i0 = 0; i0 < ITEMS; i0 += U) {
+					R r[U];
+					OffT g[U];
+#pragma unroll
+					for (int u = 0; u < U; ++u)
+						if (i0 + u < ITEMS)
+							r[u] = s_rec[tid + (i0 + u) * THREADS];
+#pragma unroll
+					for (int u = 0; u < U; ++u)
+						if (i0 + u < ITEMS)
+							g[u] = s_gadj[tile_digit<ES, DM>(p, r[u], dd)] + (OffT)(tid + (i0 + u) * THREADS);
+#pragma unroll
+					for (int u = 0; u < U; ++u)
+						if (i0 + u < ITEMS) {
+							if constexpr (ES + PL <= 4) { // streaming (evict-first) stores: 1.4 % on 4-byte keys, neutral or worse on wider records
+								if constexpr (WR)
+									__stcs(out + g[u], r[u]);
+							} else {
+								if constexpr (WR)
+									out[g[u]] = r[u];
+								if constexpr (PL != 0)
+									pout[g[u]] = s_pl[tid + (i0 + u) * THREADS];
+							}
+						}
 				}
-			}
+			};
+			if (write_rec)
+				write_full(std::true_type{});
+			else if (PL != 0)
+				write_full(std::false_type{});
 		} else {
 			for (uint32_t s = tid; s < valid; s += THREADS) {
 				const R r = s_rec[s];

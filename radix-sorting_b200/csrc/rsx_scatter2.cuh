@@ -130,6 +130,11 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter2_kerne
 	constexpr int TILE = SM::kTile;
 	constexpr int WARPS = SM::kWarps;
 	constexpr int LB = Cfg::kLookback;
+#ifdef RSX_WRITE_BATCH
+	constexpr int kWriteBatch = RSX_WRITE_BATCH;
+#else
+	constexpr int kWriteBatch = 2;
+#endif
 	constexpr uint32_t FULL = 0xFFFFFFFFu;
 	static_assert(ITEMS * 32 <= 65536, "two ranks are packed into one register");
 	static_assert(THREADS >= kBins && THREADS % 32 == 0, "one digit thread per bin: the digit scan synchronises 256 threads");
@@ -402,22 +407,41 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::kMinBlocks) scatter2_kerne
 
 		// ---- 6. coalesced per-bucket stores ----
 		if (full) {
-			constexpr int kWriteUnroll = (ITEMS % 5 == 0) ? 5 : 4;
-#pragma unroll(kWriteUnroll)
-			for (int i = 0; i < ITEMS; ++i) {
-				const uint32_t s = tid + i * THREADS;
-				const R r = s_rec[s];
-				const OffT g = s_gadj[tile_digit<ES, DM>(p, r, dd)] + (OffT)s;
-				if constexpr (ES + PL <= 4) {
-					if (write_rec)
-						__stcs(out + g, r);
-				} else {
-					if (write_rec)
-						out[g] = r;
-					if constexpr (PL != 0)
-						pout[g] = s_pl[s];
+			// batches: loads, then bucket-offset lookups, then stores (see scatter_kernel)
+			auto write_full = [&](auto wr_tag) {
+				constexpr bool WR = decltype(wr_tag)::value;
+				constexpr int U = kWriteBatch;
+#pragma unroll 1
+				for (int i0 = 0; i0 < ITEMS; i0 += U) {
+					R r[U];
+					OffT g[U];
+#pragma unroll
+					for (int u = 0; u < U; ++u)
+						if (i0 + u < ITEMS)
+							r[u] = s_rec[tid + (i0 + u) * THREADS];
+#pragma unroll
+					for (int u = 0; u < U; ++u)
+						if (i0 + u < ITEMS)
+							g[u] = s_gadj[tile_digit<ES, DM>(p, r[u], dd)] + (OffT)(tid + (i0 + u) * THREADS);
+#pragma unroll
+					for (int u = 0; u < U; ++u)
+						if (i0 + u < ITEMS) {
+							if constexpr (ES + PL <= 4) {
+								if constexpr (WR)
+									__stcs(out + g[u], r[u]);
+							} else {
+								if constexpr (WR)
+									out[g[u]] = r[u];
+								if constexpr (PL != 0)
+									pout[g[u]] = s_pl[tid + (i0 + u) * THREADS];
+							}
+						}
 				}
-			}
+			};
+			if (write_rec)
+				write_full(std::true_type{});
+			else if (PL != 0)
+				write_full(std::false_type{});
 		} else {
 			for (uint32_t s = tid; s < valid; s += THREADS) {
 				const R r = s_rec[s];
