@@ -28,6 +28,13 @@ def test_library_exports_every_declared_symbol(rsx):
         assert re.search(rf"\bT {s}\b", out), f"{s} is not a defined text symbol"
 
 
+def test_every_entry_point_is_documented():
+    """INTEGRATION.md names every entry point of include/rsx.h (with the reference interface it replaces)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [s for s in declared_symbols() if s not in doc]
+    assert not missing, f"not in INTEGRATION.md: {missing}"
+
+
 def test_version_and_strerror(rsx):
     L = rsx.lib()
     assert L.rsx_version() == 100
